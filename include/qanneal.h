@@ -1,0 +1,143 @@
+/* qanneal.h -- C ABI of libqanneal.so, the B200 (sm_100a) simulated-annealing sampler.
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * michal7kw/scRNA_seq_QAnnealing_Clustering: the QUBO/BQM sampling loop its clustering
+ * functions hand to a dimod sampler
+ *   sampler.sample_qubo(Q, ...)   Python_Functions/BQM_clustering.py:57,75,85,245,263,273
+ *                                 Python_Functions/QA_subsampling.py:42,56,65
+ *   sampler.sample(bqm, ...)      Python_Functions/BQM_clustering.py:386
+ *   sampler.sample_dqm(dqm, ...)  Python_Functions/DQM_clustering.py:45
+ *   sampler.sample_cqm(cqm, ...)  Python_Functions/CQM_clustering.py:53,89
+ * Offline that sampler is dwave-neal, whose Cython layer binds
+ *   int general_simulated_annealing(char* states, double* energies, int num_samples,
+ *        vector<double> h, vector<int> coupler_starts, vector<int> coupler_ends,
+ *        vector<double> coupler_weights, int sweeps_per_beta, vector<double> beta_schedule,
+ *        uint64_t seed, callback interrupt_callback, void* interrupt_function)
+ *   (dwave-neal neal/src/cpu_sa.h; dwave-samplers dwave/samplers/sa/src/cpu_sa.h)
+ * qa_sa_sample_ising() below is the entry point a maintainer would bind in its place.
+ *
+ * Conventions
+ *  - every function returns int: >= 0 OK, < 0 error code; message via qa_last_error()
+ *    (thread-local).  No C++ exception crosses the ABI.
+ *  - plain pointers and sizes only.  Data pointers may be HOST pointers or CUDA DEVICE
+ *    pointers of the context's device (detected with cudaPointerGetAttributes); model
+ *    and scratch memory is owned by the library, every other buffer by the caller.
+ *  - calls block until their results are complete.  A qa_ctx is not re-entrant.
+ *  - spins are int8 +1/-1, states are row-major [num_reads][n] and are IN/OUT (initial
+ *    states in, final states out), exactly like neal's `states` argument.
+ */
+#ifndef QANNEAL_H
+#define QANNEAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QA_OK 0
+#define QA_ERR_ARG (-1)      /* bad argument (sizes, null pointers, unknown enum) */
+#define QA_ERR_INDEX (-2)    /* coupler index out of range / self loop (neal: runtime_error) */
+#define QA_ERR_STATE (-3)    /* initial state not +-1 */
+#define QA_ERR_CUDA (-4)     /* CUDA runtime failure (no device, OOM, launch error) */
+#define QA_ERR_LIMIT (-5)    /* model exceeds an implementation limit */
+#define QA_ERR_INTERRUPTED (-6)
+
+/* seed_mode */
+#define QA_SEED_PER_READ 0   /* read r == neal(num_reads=1, seed=seeds[r], initial_states=states[r]) */
+#define QA_SEED_STREAM 1     /* one xorshift128+ stream across reads == neal(num_reads=R, seed=seeds[0]) */
+/* mode */
+#define QA_MODE_REFERENCE 0  /* neal's sequential variable order, bit-exact against the oracle */
+#define QA_MODE_COLOURED 1   /* graph-coloured parallel update (statistical parity only) */
+
+#define QA_MAX_GROUPS 64
+
+typedef struct qa_ctx qa_ctx;
+typedef struct qa_model qa_model;
+
+/* Counters and device-side phase timings (CUDA events on the context's stream). */
+typedef struct qa_stats {
+    uint64_t attempts;      /* n * num_sweeps * num_reads */
+    uint64_t candidates;    /* attempts with dE <  44.36142/beta  (reached the accept test) */
+    uint64_t draws;         /* xorshift128+ outputs consumed (0 < dE < threshold) */
+    uint64_t accepted;      /* spin flips performed */
+    uint64_t nbr_updates;   /* sum of deg(v) over accepted flips */
+    uint64_t active_chunks; /* 32-variable chunks that had >= 1 candidate */
+    uint64_t chunks;        /* 32-variable chunks streamed */
+    uint64_t near_ties;     /* accept tests decided by < 2^-48 relative margin */
+    double ms_h2d;          /* host->device copies (0 when inputs are device resident) */
+    double ms_build;        /* CSR construction */
+    double ms_anneal;       /* annealing kernel(s) */
+    double ms_energy;       /* energy (+argmin) kernel(s) */
+    double ms_d2h;          /* device->host copies */
+    uint32_t anneal_launches;
+    uint32_t total_launches; /* kernels of this library launched by the call */
+} qa_stats;
+
+const char *qa_last_error(void);
+int qa_version(void);
+int qa_device_count(void);
+
+/* context = one GPU + one stream + reusable scratch */
+int qa_ctx_create(int device_id, qa_ctx **out);
+int qa_ctx_destroy(qa_ctx *ctx);
+int qa_ctx_synchronize(qa_ctx *ctx);
+/* number of reads the annealing kernel keeps resident at once (one warp per read) */
+int qa_ctx_resident_reads(qa_ctx *ctx);
+
+/* Ising model, neal's vectors: h[n], couplers (starts, ends, weights)[m] in coupler order.
+ * Builds the adjacency on the device preserving neal's per-vertex push_back order. */
+int qa_model_from_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const int32_t *starts,
+                        const int32_t *ends, const double *weights, qa_model **out);
+/* Optional lazily-evaluated rank-1 terms  sum_g lambda[g]/4 * (sum_{v: grp[v]==g} coef[v]*s_v + kappa[g])^2
+ * (cut+balance, DQM cluster-size and CQM size penalties). grp[v] = -1: none. */
+int qa_model_set_groups(qa_model *model, int32_t ngroups, const int32_t *grp, const int32_t *coef,
+                        const double *lambda, const int64_t *kappa);
+int qa_model_num_variables(const qa_model *model);
+int64_t qa_model_num_couplers(const qa_model *model);
+int qa_model_max_degree(const qa_model *model);
+/* copy the device-built Ising vectors back (any pointer may be NULL) */
+int qa_model_get_ising(const qa_model *model, double *h, int32_t *starts, int32_t *ends, double *weights);
+int qa_model_destroy(qa_model *model);
+
+/* Anneal num_reads reads of a resident model.  energies_out[r] is neal's get_state_energy
+ * (spin-model energy WITHOUT offset) of the final state.  interrupt may be NULL; it is
+ * polled between read waves and a non-zero return stops the run (neal: interrupt_function);
+ * the return value is the number of reads completed. */
+typedef int (*qa_interrupt_fn)(void *user);
+int qa_sa_sample_model(qa_ctx *ctx, qa_model *model, int32_t num_reads, int8_t *states_inout,
+                       double *energies_out, int32_t num_betas, const double *beta_schedule,
+                       int32_t sweeps_per_beta, const uint64_t *seeds, int32_t seed_mode,
+                       int32_t mode, qa_interrupt_fn interrupt, void *interrupt_user,
+                       qa_stats *stats_out);
+
+/* One-shot form mirroring neal's general_simulated_annealing (model built and freed inside). */
+int qa_sa_sample_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const int32_t *starts,
+                       const int32_t *ends, const double *weights, int32_t num_reads,
+                       int8_t *states_inout, double *energies_out, int32_t num_betas,
+                       const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds,
+                       int32_t seed_mode, int32_t mode, qa_stats *stats_out);
+
+/* Many independent problems in one launch (QA_subsampling.py:24 called per sub-graph).
+ * Problem p owns variables [var_offsets[p], var_offsets[p+1]) of h and couplers
+ * [coupler_offsets[p], coupler_offsets[p+1]) (indices local to the problem); every problem
+ * runs reads_per_problem reads.  states: [num_problems][reads_per_problem][n_p] packed
+ * back to back in problem order; energies: [num_problems][reads_per_problem];
+ * seeds: [num_problems * reads_per_problem] (per-read seeding only). */
+int qa_sa_sample_ising_batch(qa_ctx *ctx, int32_t num_problems, const int64_t *var_offsets,
+                             const int64_t *coupler_offsets, const double *h, const int32_t *starts,
+                             const int32_t *ends, const double *weights, int32_t reads_per_problem,
+                             int8_t *states_inout, double *energies_out, int32_t num_betas,
+                             const double *beta_schedule, int32_t sweeps_per_beta,
+                             const uint64_t *seeds, qa_stats *stats_out);
+
+/* Energies of given states in neal's summation order + warp-shuffle min/argmin
+ * (neal get_state_energy, dimod bqm.energies, SampleSet.first). Outputs may be NULL. */
+int qa_energy_argmin(qa_ctx *ctx, qa_model *model, int32_t num_reads, const int8_t *states,
+                     double *energies_out, double *best_energy, int64_t *best_index,
+                     qa_stats *stats_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QANNEAL_H */

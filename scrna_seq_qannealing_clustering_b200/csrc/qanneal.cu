@@ -1,0 +1,1258 @@
+// qanneal.cu -- libqanneal.so: hand-written sm_100a simulated annealing for the clustering QUBOs of
+// michal7kw/scRNA_seq_QAnnealing_Clustering (C ABI in include/qanneal.h).
+//
+// What it replaces (reference file:line -> upstream algorithm):
+//   sampler.sample_qubo / .sample / .sample_dqm / .sample_cqm call sites
+//     Python_Functions/BQM_clustering.py:57,75,85,245,263,273,386; QA_subsampling.py:42,56,65;
+//     DQM_clustering.py:45; CQM_clustering.py:53,89
+//   -> dwave-neal neal/src/cpu_sa.cpp: general_simulated_annealing / simulated_annealing_run /
+//      get_flip_energy / get_state_energy / FASTRAND.
+//
+// Design (B200-first, not a translation of the CPU loop):
+//   * one WARP per read.  The read's local fields f[v] = h_v + sum_j J_vj s_j live in HBM as fp64 and
+//     are streamed 32 variables (256 B) at a time with ld.global.cg + prefetch.global.L2 run-ahead;
+//     spins are bit-packed (1 bit/attempt of traffic).  neal's dE[v] is recovered exactly as
+//     -2*s_v*f[v] (scaling by +-2 commutes with rounding), so a flip needs no read of s_j: every
+//     neighbour update is one fire-and-forget  red.global.add.f64 f[j], -2*s_v*J  performed in L2.
+//   * the 32 lanes of a chunk decide "candidate" (dE < 44.36142/beta) in parallel; candidates are then
+//     resolved in variable order with a warp-uniform xorshift128+ stream, so the sequence of RNG
+//     draws, accepts and fp64 roundings is exactly neal's.  In-chunk neighbours are patched in
+//     registers by shuffles in neighbour order.
+//   * persistent grid (multiple of the SM count), reads pulled from an atomic counter; only the
+//     resident warps own fp64 scratch (n*8 B each), so 100k reads x 131k variables need ~5 GB, not 118.
+//   * optional rank-1 "group" terms evaluated lazily from per-warp integer counters in shared memory.
+//   * energies are evaluated by a thread-per-read kernel in neal's summation order on a
+//     read-transposed packed-spin layout (coalesced), followed by a warp-shuffle argmin.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see __graft_entry__.build()).
+
+#include "../../include/qanneal.h"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define QA_VERSION 100
+#define FULL_MASK 0xffffffffu
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define QA_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(QA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side problem description (one per independent problem; a plain model is a batch of one)
+// ------------------------------------------------------------------------------------------------
+struct ProblemDesc {
+    int32_t n;        // variables
+    int32_t nch;      // 32-variable chunks = ceil(n/32)
+    int32_t ngroups;  // rank-1 groups (0: none)
+    int32_t reads;    // reads of this problem
+    int32_t rpad;     // reads padded to a multiple of 32 (stride of packedT)
+    int32_t pad_;
+    int64_t m;        // couplers
+    int64_t read_base;  // index of this problem's read 0 in the global read numbering
+    const int32_t *rowptr;  // [nch*32 + 1] entries valid (padding rows are empty)
+    const int32_t *col;     // CSR neighbour, local variable index
+    const double *val;      // CSR coupling
+    const double *h;        // [n]
+    const int32_t *starts;  // COO in caller order (energy summation order)
+    const int32_t *ends;
+    const double *w;
+    const int32_t *grp;     // [nch*32] or null
+    const int32_t *coef;    // [nch*32]
+    const double *lambda;   // [ngroups]
+    const long long *kappa; // [ngroups]
+    int8_t *states;         // [reads][n]
+    uint32_t *packedT;      // [nch][rpad] final spins, bit i of word (c, r) = spin of variable 32c+i (1: +1)
+    double *energies;       // [reads]
+};
+
+struct AnnealParams {
+    const ProblemDesc *descs;
+    int32_t num_problems;
+    int32_t reads_per_problem;   // uniform (batch) ; == total reads for a single model
+    int64_t total_reads;
+    const double *betas;
+    int32_t num_betas;
+    int32_t sweeps_per_beta;
+    const unsigned long long *seeds;
+    int32_t seed_mode;
+    double *f_scratch;           // [slots][f_stride]
+    uint32_t *spw_scratch;       // [slots][spw_stride]
+    int64_t f_stride;
+    int64_t spw_stride;
+    unsigned long long *counter; // next read to hand out
+    unsigned long long *stats;   // QA_NSTAT counters
+    int *error_flag;
+    int64_t read_begin;          // wave support: global read range [read_begin, read_end)
+    int64_t read_end;
+};
+
+enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
+
+constexpr int QA_TPB_MAX = 256;
+constexpr int QA_PREFETCH_CHUNKS = 16;  // run-ahead distance of the L2 prefetch, in 256-byte chunks
+constexpr double QA_TWO64 = 18446744073709551616.0;
+
+__device__ __forceinline__ unsigned long long rng_next(unsigned long long &s0, unsigned long long &s1) {
+    // neal FASTRAND (xorshift128+)
+    unsigned long long x = s0;
+    const unsigned long long y = s1;
+    s0 = y;
+    x ^= x << 23;
+    s1 = x ^ y ^ (x >> 17) ^ (y >> 26);
+    return s1 + y;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ void red_add_f64(double *addr, double v) {
+    // fire-and-forget fp64 reduction performed at L2 (RED.E.ADD.F64); round-to-nearest like the CPU add
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+struct WarpStats {
+    unsigned long long cand, draws, acc, nbr, active, chunks, ties;
+};
+
+// ------------------------------------------------------------------------------------------------
+// one read, reference order.  Restates neal simulated_annealing_run() for one `state`.
+// ------------------------------------------------------------------------------------------------
+template <bool GROUPS>
+__device__ void anneal_read(const ProblemDesc &D, const AnnealParams &P, int64_t r_local, double *__restrict__ f,
+                            uint32_t *__restrict__ spw, unsigned long long &s0, unsigned long long &s1,
+                            long long *Mw, WarpStats &st, int *error_flag) {
+    const int lane = threadIdx.x & 31;
+    const int n = D.n;
+    const int nch = D.nch;
+    int8_t *state_row = D.states + r_local * (int64_t)n;
+
+    // ---- pack the initial +-1 bytes into spin words (bit = 1 <=> s = +1); padding variables are +1
+    for (int cb = 0; cb < nch; cb += 32) {
+        uint32_t wg = 0xffffffffu;
+        const int cend = min(32, nch - cb);
+        for (int k = 0; k < cend; ++k) {
+            const int v = (cb + k) * 32 + lane;
+            int s = 1;
+            if (v < n) {
+                s = state_row[v];
+                if (s != 1 && s != -1) atomicExch(error_flag, QA_ERR_STATE);
+            }
+            const uint32_t w = __ballot_sync(FULL_MASK, s > 0);
+            if (lane == k) wg = w;
+        }
+        __stcg(spw + cb + lane, wg);
+    }
+    __syncwarp();
+
+    // ---- local fields, neal get_flip_energy(): energy = h[v]; for nbr in adjacency order: energy += s_nbr*J
+    for (int c = 0; c < nch; ++c) {
+        const int v = c * 32 + lane;
+        double fv = -INFINITY;  // padding: dE = -2*(+1)*(-inf) = +inf, never a candidate
+        if (v < n) {
+            fv = D.h[v];
+            const int e0 = D.rowptr[v], e1 = D.rowptr[v + 1];
+            for (int e = e0; e < e1; ++e) {
+                const int j = D.col[e];
+                const uint32_t wj = __ldcg(spw + (j >> 5));
+                const double J = D.val[e];
+                fv += ((wj >> (j & 31)) & 1u) ? J : -J;
+            }
+        }
+        __stcg(f + v, fv);
+    }
+    if (GROUPS) {
+        for (int g = lane; g < D.ngroups; g += 32) Mw[g] = 0;
+        __syncwarp();
+        for (int c = 0; c < nch; ++c) {
+            const int v = c * 32 + lane;
+            const int g = D.grp[v];
+            if (g >= 0) {
+                const uint32_t wv = __ldcg(spw + c);
+                const long long a = D.coef[v];
+                atomicAdd(reinterpret_cast<unsigned long long *>(Mw + g),
+                          (unsigned long long)(((wv >> lane) & 1u) ? a : -a));
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- the anneal: for beta: for sweep: for var (neal order)
+    for (int b = 0; b < P.num_betas; ++b) {
+        const double beta = P.betas[b];
+        const double thr = 44.36142 / beta;
+        for (int sw = 0; sw < P.sweeps_per_beta; ++sw) {
+            uint32_t wg = 0;
+            bool gdirty = false;
+            for (int c = 0; c < nch; ++c) {
+                const int k = c & 31;
+                if (k == 0) {
+                    wg = __ldcg(spw + c + lane);
+                    gdirty = false;
+                }
+                if ((lane & 15) == 0) {
+                    int cp = c + QA_PREFETCH_CHUNKS;
+                    if (cp >= nch) cp %= nch;
+                    prefetch_l2(f + cp * 32 + lane);
+                }
+                const int v = c * 32 + lane;
+                double fv = __ldcg(f + v);
+                uint32_t w = __shfl_sync(FULL_MASK, wg, k);
+                int g = -1;
+                long long a = 0, kap = 0;
+                double lam = 0.0;
+                if (GROUPS) {
+                    g = __ldg(D.grp + v);
+                    if (g >= 0) {
+                        a = __ldg(D.coef + v);
+                        lam = __ldg(D.lambda + g);
+                        kap = __ldg(D.kappa + g);
+                    }
+                }
+                // neal's delta_energy[v] == -2*s_v*f[v] exactly; plus the lazily evaluated rank-1 cost
+                auto flip_cost = [&](uint32_t word) -> double {
+                    const bool up = (word >> lane) & 1u;
+                    double d = up ? -2.0 * fv : 2.0 * fv;
+                    if (GROUPS) {
+                        if (g >= 0) {
+                            const long long t = a * (a - (up ? 1 : -1) * (Mw[g] + kap));
+                            d = d + lam * (double)t;
+                        }
+                    }
+                    return d;
+                };
+                double dE = flip_cost(w);
+                bool cand = !(dE >= thr);  // neal: if (delta_energy[var] >= threshold) continue;
+                uint32_t pend = __ballot_sync(FULL_MASK, cand);
+                if (pend) {
+                    st.active++;
+                    const int e0 = __ldg(D.rowptr + v), e1 = __ldg(D.rowptr + v + 1);
+                    bool pvalid = false;
+                    double p = 0.0;
+                    while (pend) {
+                        const int l = __ffs(pend) - 1;
+                        pend &= pend - 1;
+                        st.cand++;
+                        const double dEl = __shfl_sync(FULL_MASK, dE, l);
+                        bool acc = true;
+                        if (dEl > 0.0) {
+                            const uint32_t pv = __ballot_sync(FULL_MASK, pvalid);
+                            if (!((pv >> l) & 1u)) {
+                                // exp(-dE*beta)*2^64 for every lane that may need it (one SIMT pass)
+                                if (!pvalid && cand && dE > 0.0) p = exp(-dE * beta) * QA_TWO64;
+                                pvalid = true;
+                            }
+                            const unsigned long long rnd = rng_next(s0, s1);
+                            st.draws++;
+                            const double pl = __shfl_sync(FULL_MASK, p, l);
+                            const double rd = __ull2double_rn(rnd);
+                            acc = pl > rd;  // neal: exp(-dE*beta) * RANDMAX > rand
+                            if (fabs(pl - rd) <= pl * 3.5527136788005009e-15) st.ties++;
+                        }
+                        if (acc) {
+                            st.acc++;
+                            const int r0 = __shfl_sync(FULL_MASK, e0, l);
+                            const int r1 = __shfl_sync(FULL_MASK, e1, l);
+                            const bool up_l = (w >> l) & 1u;
+                            const double cf = up_l ? -2.0 : 2.0;  // f[j] += -2*s_l*J  <=> dE[j] += 4*s_l*J*s_j
+                            st.nbr += (unsigned long long)(r1 - r0);
+                            uint32_t touched = 0;
+                            for (int base = r0; base < r1; base += 32) {
+                                const int e = base + lane;
+                                const bool valid = e < r1;
+                                int j = -1;
+                                double d = 0.0;
+                                if (valid) {
+                                    j = __ldg(D.col + e);
+                                    d = cf * __ldg(D.val + e);
+                                    red_add_f64(f + j, d);
+                                }
+                                uint32_t inm = __ballot_sync(FULL_MASK, valid && (j >> 5) == c);
+                                while (inm) {  // patch register copies of this chunk, in neighbour order
+                                    const int kk = __ffs(inm) - 1;
+                                    inm &= inm - 1;
+                                    const int tj = __shfl_sync(FULL_MASK, j, kk) & 31;
+                                    const double dk = __shfl_sync(FULL_MASK, d, kk);
+                                    if (lane == tj) fv += dk;
+                                    touched |= 1u << tj;
+                                }
+                            }
+                            w ^= 1u << l;
+                            gdirty = true;
+                            if (lane == k) wg = w;
+                            if (GROUPS) {
+                                const int gl = __shfl_sync(FULL_MASK, g, l);
+                                if (gl >= 0) {
+                                    const long long al = __shfl_sync(FULL_MASK, a, l);
+                                    __syncwarp();
+                                    if (lane == 0) Mw[gl] -= 2 * al * (up_l ? 1 : -1);
+                                    __syncwarp();
+                                    touched |= __ballot_sync(FULL_MASK, g == gl);
+                                }
+                            }
+                            if ((touched >> lane) & 1u) pvalid = false;
+                            dE = flip_cost(w);
+                            cand = !(dE >= thr);
+                            pend = __ballot_sync(FULL_MASK, cand) & ~((2u << l) - 1u);
+                        }
+                    }
+                    __syncwarp();  // order this chunk's reductions before later loads of the same addresses
+                }
+                if ((k == 31 || c == nch - 1) && gdirty) __stcg(spw + (c & ~31) + lane, wg);
+            }
+            st.chunks += (unsigned long long)nch;
+        }
+    }
+    __syncwarp();
+
+    // ---- results: +-1 bytes back into the caller's row, packed transposed copy for the energy kernel
+    for (int c = 0; c < nch; ++c) {
+        const int v = c * 32 + lane;
+        const uint32_t w = __ldcg(spw + c);
+        if (v < n) state_row[v] = ((w >> lane) & 1u) ? 1 : -1;
+    }
+    for (int c = lane; c < nch; c += 32) D.packedT[(int64_t)c * D.rpad + r_local] = __ldcg(spw + c);
+}
+
+template <bool GROUPS>
+__global__ void __launch_bounds__(QA_TPB_MAX, 4) k_anneal_ref(AnnealParams P) {
+    __shared__ long long Msh[GROUPS ? (QA_TPB_MAX / 32) * QA_MAX_GROUPS : 1];
+    __shared__ unsigned long long next_read[QA_TPB_MAX / 32];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    double *f = P.f_scratch + slot * P.f_stride;
+    uint32_t *spw = P.spw_scratch + slot * P.spw_stride;
+    long long *Mw = GROUPS ? (Msh + wib * QA_MAX_GROUPS) : Msh;
+    WarpStats st = {0, 0, 0, 0, 0, 0, 0};
+
+    if (P.seed_mode == QA_SEED_STREAM) {
+        // one xorshift128+ stream across reads (neal num_reads=R): inherently serial, validation only
+        if (slot != 0) return;
+        unsigned long long s0 = P.seeds[0] ? P.seeds[0] : ~0ull, s1 = 0;
+        for (int64_t r = P.read_begin; r < P.read_end; ++r) {
+            const int p = (int)(r / P.reads_per_problem);
+            const ProblemDesc D = P.descs[p];
+            anneal_read<GROUPS>(D, P, r - D.read_base, f, spw, s0, s1, Mw, st, P.error_flag);
+        }
+    } else {
+        for (;;) {
+            if (lane == 0) next_read[wib] = P.read_begin + atomicAdd(P.counter, 1ull);
+            __syncwarp();
+            const int64_t r = (int64_t)next_read[wib];
+            __syncwarp();
+            if (r >= P.read_end) break;
+            const int p = (int)(r / P.reads_per_problem);
+            const ProblemDesc D = P.descs[p];
+            const unsigned long long sd = P.seeds[r];
+            unsigned long long s0 = sd ? sd : ~0ull, s1 = 0;  // neal: rng_state = {seed ? seed : RANDMAX, 0}
+            anneal_read<GROUPS>(D, P, r - D.read_base, f, spw, s0, s1, Mw, st, P.error_flag);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(P.stats + ST_CAND, st.cand);
+        atomicAdd(P.stats + ST_DRAWS, st.draws);
+        atomicAdd(P.stats + ST_ACC, st.acc);
+        atomicAdd(P.stats + ST_NBR, st.nbr);
+        atomicAdd(P.stats + ST_ACTIVE, st.active);
+        atomicAdd(P.stats + ST_CHUNKS, st.chunks);
+        atomicAdd(P.stats + ST_TIES, st.ties);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// energies: neal get_state_energy(), one thread per read, reads on lanes (coalesced packedT loads)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_energy(const ProblemDesc *descs) {
+    const ProblemDesc D = descs[blockIdx.y];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= D.reads) return;
+    const uint32_t *pk = D.packedT + r;
+    const int64_t stride = D.rpad;
+    double E = 0.0;
+    for (int c = 0; c < D.nch; ++c) {
+        const uint32_t w = pk[c * stride];
+        const int base = c * 32;
+        const int lim = min(32, D.n - base);
+        for (int i = 0; i < lim; ++i) {
+            const double hv = __ldg(D.h + base + i);
+            E += ((w >> i) & 1u) ? hv : -hv;  // state[v]*h[v]
+        }
+    }
+    for (int64_t e = 0; e < D.m; ++e) {
+        const int u = __ldg(D.starts + e), v = __ldg(D.ends + e);
+        const double wt = __ldg(D.w + e);
+        const uint32_t bu = (pk[(int64_t)(u >> 5) * stride] >> (u & 31)) & 1u;
+        const uint32_t bv = (pk[(int64_t)(v >> 5) * stride] >> (v & 31)) & 1u;
+        E += (bu ^ bv) ? -wt : wt;  // state[u]*w*state[v]
+    }
+    for (int g = 0; g < D.ngroups; ++g) {
+        long long M = 0;
+        for (int c = 0; c < D.nch; ++c) {
+            const uint32_t w = pk[c * stride];
+            for (int i = 0; i < 32; ++i) {
+                const int v = c * 32 + i;
+                if (__ldg(D.grp + v) == g) {
+                    const long long a = __ldg(D.coef + v);
+                    M += ((w >> i) & 1u) ? a : -a;
+                }
+            }
+        }
+        const long long t = M + D.kappa[g];
+        E += D.lambda[g] * (double)(t * t) * 0.25;
+    }
+    D.energies[r] = E;
+}
+
+// pack caller-provided +-1 states into the read-transposed layout (for qa_energy_argmin)
+__global__ void k_pack_states(ProblemDesc D, int *error_flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= D.reads) return;
+    const int8_t *row = D.states + r * (int64_t)D.n;
+    for (int c = 0; c < D.nch; ++c) {
+        const int v = c * 32 + lane;
+        int s = 1;
+        if (v < D.n) {
+            s = row[v];
+            if (s != 1 && s != -1) atomicExch(error_flag, QA_ERR_STATE);
+        }
+        const uint32_t w = __ballot_sync(FULL_MASK, s > 0);
+        if (lane == 0) D.packedT[(int64_t)c * D.rpad + r] = w;
+    }
+}
+
+// warp-shuffle min / argmin (lowest index wins ties, like a stable sort by energy -> SampleSet.first)
+__global__ void __launch_bounds__(1024) k_argmin(const double *energies, int64_t count, double *best_e, long long *best_i) {
+    __shared__ double se[32];
+    __shared__ long long si[32];
+    double e = INFINITY;
+    long long idx = 0x7fffffffffffffffll;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
+        const double x = energies[i];
+        if (x < e || (x == e && i < idx)) { e = x; idx = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oe = __shfl_xor_sync(FULL_MASK, e, off);
+        const long long oi = __shfl_xor_sync(FULL_MASK, idx, off);
+        if (oe < e || (oe == e && oi < idx)) { e = oe; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { se[threadIdx.x >> 5] = e; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        e = threadIdx.x < nw ? se[threadIdx.x] : INFINITY;
+        idx = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffffffffffffll;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double oe = __shfl_xor_sync(FULL_MASK, e, off);
+            const long long oi = __shfl_xor_sync(FULL_MASK, idx, off);
+            if (oe < e || (oe == e && oi < idx)) { e = oe; idx = oi; }
+        }
+        if (threadIdx.x == 0) { *best_e = e; *best_i = idx; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjacency construction on the device, preserving neal's push_back order (stable sort by vertex)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_make_entries(int64_t m_total, int32_t num_problems, const int64_t *var_off, const int64_t *cpl_off,
+                               const int32_t *starts, const int32_t *ends, uint32_t *keys, uint32_t *vals, int *error_flag) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m_total) return;
+    // problem of coupler c (binary search in coupler offsets)
+    int lo = 0, hi = num_problems;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cpl_off[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int64_t vbase = var_off[lo];
+    const int64_t np = var_off[lo + 1] - vbase;
+    const int u = starts[c], v = ends[c];
+    if (u < 0 || v < 0 || u >= np || v >= np || u == v) {
+        atomicExch(error_flag, QA_ERR_INDEX);
+        keys[2 * c] = keys[2 * c + 1] = 0;
+        vals[2 * c] = (uint32_t)(2 * c);
+        vals[2 * c + 1] = (uint32_t)(2 * c + 1);
+        return;
+    }
+    keys[2 * c] = (uint32_t)(vbase + u);      // entry 2c   : row u, neighbour v
+    keys[2 * c + 1] = (uint32_t)(vbase + v);  // entry 2c+1 : row v, neighbour u
+    vals[2 * c] = (uint32_t)(2 * c);
+    vals[2 * c + 1] = (uint32_t)(2 * c + 1);
+}
+
+__global__ void k_fill_csr(int64_t entries, const uint32_t *sorted_vals, const int32_t *starts, const int32_t *ends,
+                           const double *w, int32_t *col, double *val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= entries) return;
+    const uint32_t e = sorted_vals[i];
+    const int64_t c = e >> 1;
+    col[i] = (e & 1u) ? starts[c] : ends[c];
+    val[i] = w[c];
+}
+
+// rowptr[x] = first sorted position whose key >= x  (x in [0, rows]); rows beyond are clamped to `entries`
+__global__ void k_rowptr(int64_t rows_alloc, int64_t entries, const uint32_t *sorted_keys, int32_t *rowptr, int *maxdeg) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= rows_alloc) return;
+    int64_t lo = 0, hi = entries;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)sorted_keys[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    rowptr[x] = (int32_t)lo;
+    // degree of row x-1 is rowptr[x]-rowptr[x-1]; computed by the thread of x via a second search
+    if (x > 0) {
+        int64_t lo2 = 0, hi2 = entries;
+        while (lo2 < hi2) {
+            const int64_t mid = (lo2 + hi2) >> 1;
+            if ((int64_t)sorted_keys[mid] < x - 1) lo2 = mid + 1; else hi2 = mid;
+        }
+        atomicMax(maxdeg, (int)(lo - lo2));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct qa_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf f, spw, states, energies, seeds, betas, packed, misc, cubtmp;
+    unsigned long long *d_stats = nullptr;  // QA_NSTAT counters + 1 read counter
+    int *d_flag = nullptr;
+    double *d_best_e = nullptr;
+    long long *d_best_i = nullptr;
+    uint32_t launches = 0;
+};
+
+struct qa_model {
+    qa_ctx *ctx = nullptr;
+    int32_t num_problems = 1;
+    int64_t n_total = 0;   // sum of n_p
+    int64_t m_total = 0;
+    int32_t n_max = 0, nch_max = 0;
+    int32_t max_deg = 0;
+    int32_t ngroups = 0;
+    std::vector<int64_t> var_off, cpl_off;  // host copies [P+1]
+    // device arrays (owned)
+    double *h = nullptr;
+    int32_t *starts = nullptr, *ends = nullptr;
+    double *w = nullptr;
+    int32_t *rowptr = nullptr, *col = nullptr;
+    double *val = nullptr;
+    int32_t *grp = nullptr, *coef = nullptr;
+    double *lambda = nullptr;
+    long long *kappa = nullptr;
+    ProblemDesc *d_descs = nullptr;
+    std::vector<ProblemDesc> descs;  // host mirror (pointers are device pointers)
+};
+
+namespace {
+
+int ensure(DevBuf &b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return QA_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    if (bytes == 0) bytes = 256;
+    QA_CUDA(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return QA_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+template <typename T>
+int upload(qa_ctx *ctx, T **dst, const T *src, size_t count) {
+    *dst = nullptr;
+    QA_CUDA(cudaMalloc((void **)dst, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count)
+        QA_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyDefault, ctx->stream));
+    return QA_OK;
+}
+
+// build CSR (all problems at once) from the device COO already stored in the model
+int build_adjacency(qa_model *M) {
+    qa_ctx *ctx = M->ctx;
+    const int64_t m = M->m_total;
+    const int64_t entries = 2 * m;
+    const int64_t rows_alloc = M->n_total + 64 + 1;  // padding rows read by the last chunk of the last problem
+    if (entries >= (int64_t)0x7fffffff) return fail(QA_ERR_LIMIT, "more than 2^30 couplers: use a structured (group) model");
+    if (M->n_total >= (int64_t)0x7fffffff) return fail(QA_ERR_LIMIT, "too many variables");
+    QA_CUDA(cudaMalloc((void **)&M->rowptr, rows_alloc * sizeof(int32_t)));
+    QA_CUDA(cudaMalloc((void **)&M->col, std::max<int64_t>(entries, 1) * sizeof(int32_t)));
+    QA_CUDA(cudaMalloc((void **)&M->val, std::max<int64_t>(entries, 1) * sizeof(double)));
+    QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
+    int64_t *d_off = nullptr;
+    const int P = M->num_problems;
+    QA_CUDA(cudaMalloc((void **)&d_off, 2 * (P + 1) * sizeof(int64_t)));
+    QA_CUDA(cudaMemcpyAsync(d_off, M->var_off.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(d_off + P + 1, M->cpl_off.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    int rc = QA_OK;
+    if (entries > 0) {
+        int rc2 = ensure(ctx->misc, (size_t)entries * 4 * sizeof(uint32_t));
+        if (rc2) { cudaFree(d_off); return rc2; }
+        keys = (uint32_t *)ctx->misc.p;
+        vals = keys + entries;
+        keys2 = vals + entries;
+        vals2 = keys2 + entries;
+        const int tpb = 256;
+        k_make_entries<<<(unsigned)((m + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(m, P, d_off, d_off + P + 1, M->starts, M->ends,
+                                                                                 keys, vals, ctx->d_flag);
+        ctx->launches++;
+        int end_bit = 1;
+        while (((int64_t)1 << end_bit) < M->n_total + 1 && end_bit < 32) ++end_bit;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)entries, 0, end_bit, ctx->stream);
+        rc2 = ensure(ctx->cubtmp, tmp_bytes);
+        if (rc2) { cudaFree(d_off); return rc2; }
+        cudaError_t ce = cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, tmp_bytes, keys, keys2, vals, vals2, (int)entries, 0,
+                                                         end_bit, ctx->stream);
+        if (ce != cudaSuccess) { cudaFree(d_off); return fail(QA_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(ce)); }
+        ctx->launches += 4;
+        k_fill_csr<<<(unsigned)((entries + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(entries, vals2, M->starts, M->ends, M->w, M->col, M->val);
+        ctx->launches++;
+    } else {
+        int rc2 = ensure(ctx->misc, 256);
+        if (rc2) { cudaFree(d_off); return rc2; }
+        keys2 = (uint32_t *)ctx->misc.p;
+    }
+    {
+        const int tpb = 256;
+        k_rowptr<<<(unsigned)((rows_alloc + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(rows_alloc, entries, keys2, M->rowptr, ctx->d_flag + 1);
+        ctx->launches++;
+    }
+    int flags[2] = {0, 0};
+    cudaError_t ce = cudaMemcpyAsync(flags, ctx->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_off);
+    if (ce != cudaSuccess) return fail(QA_ERR_CUDA, std::string("adjacency build: ") + cudaGetErrorString(ce));
+    if (flags[0] != 0) return fail(QA_ERR_INDEX, "coupler index out of range or self-loop");
+    M->max_deg = flags[1];
+    return rc;
+}
+
+int finalize_descs(qa_model *M) {
+    const int P = M->num_problems;
+    M->descs.assign(P, ProblemDesc());
+    M->n_max = 0;
+    for (int p = 0; p < P; ++p) {
+        ProblemDesc &D = M->descs[p];
+        const int64_t v0 = M->var_off[p], c0 = M->cpl_off[p];
+        D.n = (int32_t)(M->var_off[p + 1] - v0);
+        D.nch = (D.n + 31) / 32;
+        D.ngroups = 0;
+        D.m = M->cpl_off[p + 1] - c0;
+        D.rowptr = M->rowptr + v0;
+        D.col = M->col;   // rowptr holds global entry positions
+        D.val = M->val;
+        D.h = M->h + v0;
+        D.starts = M->starts + c0;
+        D.ends = M->ends + c0;
+        D.w = M->w + c0;
+        D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
+        M->n_max = std::max(M->n_max, D.n);
+    }
+    M->nch_max = (M->n_max + 31) / 32;
+    if (!M->d_descs) QA_CUDA(cudaMalloc((void **)&M->d_descs, P * sizeof(ProblemDesc)));
+    return QA_OK;
+}
+
+int model_create(qa_ctx *ctx, int32_t P, const int64_t *var_off, const int64_t *cpl_off, const double *h,
+                 const int32_t *starts, const int32_t *ends, const double *w, qa_model **out) {
+    qa_model *M = new qa_model();
+    M->ctx = ctx;
+    M->num_problems = P;
+    M->var_off.assign(var_off, var_off + P + 1);
+    M->cpl_off.assign(cpl_off, cpl_off + P + 1);
+    M->n_total = var_off[P];
+    M->m_total = cpl_off[P];
+    int rc = upload(ctx, &M->h, h, (size_t)M->n_total);
+    if (!rc) rc = upload(ctx, &M->starts, starts, (size_t)M->m_total);
+    if (!rc) rc = upload(ctx, &M->ends, ends, (size_t)M->m_total);
+    if (!rc) rc = upload(ctx, &M->w, w, (size_t)M->m_total);
+    if (!rc) rc = build_adjacency(M);
+    if (!rc) rc = finalize_descs(M);
+    if (rc) {
+        qa_model_destroy(M);
+        return rc;
+    }
+    *out = M;
+    return QA_OK;
+}
+
+struct RunBuffers {
+    int8_t *d_states = nullptr;
+    double *d_energies = nullptr;
+    bool states_on_host = false, energies_on_host = false;
+};
+
+int check_schedule(int32_t num_betas, const double *betas, int32_t sweeps_per_beta) {
+    if (num_betas < 0 || sweeps_per_beta < 0) return fail(QA_ERR_ARG, "negative schedule size");
+    if (num_betas > 0 && !betas) return fail(QA_ERR_ARG, "beta_schedule is null");
+    return QA_OK;
+}
+
+// core: anneal all reads of all problems of a model; states/energies already on the device
+int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_states, double *d_energies,
+               int32_t num_betas, const double *d_betas, int32_t sweeps_per_beta, const unsigned long long *d_seeds,
+               int32_t seed_mode, qa_interrupt_fn interrupt, void *iuser, qa_stats *st, int64_t *completed) {
+    const int P = M->num_problems;
+    const int64_t total_reads = (int64_t)P * reads_per_problem;
+    const int32_t rpad = (reads_per_problem + 31) & ~31;
+    *completed = 0;
+    if (total_reads == 0) return QA_OK;
+
+    // packed transposed spins for the energy kernel
+    size_t packed_words = 0;
+    for (int p = 0; p < P; ++p) packed_words += (size_t)M->descs[p].nch * rpad;
+    int rc = ensure(ctx->packed, std::max<size_t>(packed_words, 1) * sizeof(uint32_t));
+    if (rc) return rc;
+    {
+        size_t off = 0;
+        int64_t st_off = 0;
+        for (int p = 0; p < P; ++p) {
+            ProblemDesc &D = M->descs[p];
+            D.reads = reads_per_problem;
+            D.rpad = rpad;
+            D.read_base = (int64_t)p * reads_per_problem;
+            D.states = d_states + st_off;
+            D.packedT = (uint32_t *)ctx->packed.p + off;
+            D.energies = d_energies + (int64_t)p * reads_per_problem;
+            off += (size_t)D.nch * rpad;
+            st_off += (int64_t)reads_per_problem * D.n;
+        }
+        QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
+    }
+
+    // launch geometry: persistent grid, one warp per resident read
+    const bool groups = M->ngroups > 0;
+    int wpb = QA_TPB_MAX / 32;
+    if (seed_mode == QA_SEED_STREAM) wpb = 1;
+    else if (total_reads < (int64_t)ctx->num_sms * wpb) wpb = (int)std::max<int64_t>(1, (total_reads + ctx->num_sms - 1) / ctx->num_sms);
+    const int tpb = wpb * 32;
+    int bps = 0;
+    if (groups) QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<true>, tpb, 0));
+    else QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<false>, tpb, 0));
+    if (bps < 1) return fail(QA_ERR_CUDA, "annealing kernel does not fit on an SM");
+    int64_t grid = (int64_t)bps * ctx->num_sms;  // multiple of the SM count
+    const int64_t need = (total_reads + wpb - 1) / wpb;
+    if (need < grid) grid = need;
+    if (seed_mode == QA_SEED_STREAM) grid = 1;
+    const int64_t slots = grid * wpb;
+    const int64_t f_stride = (int64_t)M->nch_max * 32;
+    const int64_t spw_stride = ((int64_t)M->nch_max + 31) & ~31ll;
+    rc = ensure(ctx->f, (size_t)slots * f_stride * sizeof(double));
+    if (!rc) rc = ensure(ctx->spw, (size_t)slots * spw_stride * sizeof(uint32_t));
+    if (rc) return rc;
+
+    QA_CUDA(cudaMemsetAsync(ctx->d_stats, 0, (QA_NSTAT + 1) * sizeof(unsigned long long), ctx->stream));
+    QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
+
+    AnnealParams A;
+    A.descs = M->d_descs;
+    A.num_problems = P;
+    A.reads_per_problem = reads_per_problem;
+    A.total_reads = total_reads;
+    A.betas = d_betas;
+    A.num_betas = num_betas;
+    A.sweeps_per_beta = sweeps_per_beta;
+    A.seeds = d_seeds;
+    A.seed_mode = seed_mode;
+    A.f_scratch = (double *)ctx->f.p;
+    A.spw_scratch = (uint32_t *)ctx->spw.p;
+    A.f_stride = f_stride;
+    A.spw_stride = spw_stride;
+    A.counter = ctx->d_stats + QA_NSTAT;
+    A.stats = ctx->d_stats;
+    A.error_flag = ctx->d_flag;
+
+    // without an interrupt callback the whole job is one launch; with one, read waves of `slots` reads
+    const int64_t wave = (interrupt && seed_mode != QA_SEED_STREAM) ? slots : total_reads;
+    QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    int64_t done = 0;
+    bool interrupted = false;
+    while (done < total_reads) {
+        A.read_begin = done;
+        A.read_end = std::min(total_reads, done + wave);
+        QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
+        if (groups) k_anneal_ref<true><<<(unsigned)grid, tpb, 0, ctx->stream>>>(A);
+        else k_anneal_ref<false><<<(unsigned)grid, tpb, 0, ctx->stream>>>(A);
+        QA_CUDA(cudaGetLastError());
+        ctx->launches++;
+        if (st) st->anneal_launches++;
+        done = A.read_end;
+        if (interrupt && done < total_reads) {
+            QA_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (interrupt(iuser)) { interrupted = true; break; }
+        }
+    }
+    QA_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    {
+        dim3 g((unsigned)((reads_per_problem + 127) / 128), (unsigned)P);
+        k_energy<<<g, 128, 0, ctx->stream>>>(M->d_descs);
+        QA_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    QA_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    int flag = 0;
+    unsigned long long hs[QA_NSTAT + 1];
+    QA_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(hs, ctx->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flag != 0) return fail(flag, "initial states must be +1/-1");
+    if (st) {
+        st->candidates += hs[ST_CAND];
+        st->draws += hs[ST_DRAWS];
+        st->accepted += hs[ST_ACC];
+        st->nbr_updates += hs[ST_NBR];
+        st->active_chunks += hs[ST_ACTIVE];
+        st->chunks += hs[ST_CHUNKS];
+        st->near_ties += hs[ST_TIES];
+        st->ms_anneal += elapsed(ctx->ev[2], ctx->ev[3]);
+        st->ms_energy += elapsed(ctx->ev[3], ctx->ev[4]);
+        uint64_t att = 0;
+        for (int p = 0; p < P; ++p) att += (uint64_t)M->descs[p].n;
+        st->attempts += att * (uint64_t)num_betas * (uint64_t)sweeps_per_beta * (uint64_t)(done / P);
+    }
+    *completed = done;
+    (void)interrupted;
+    return QA_OK;
+}
+
+// stage caller buffers (host or device), run, and return results
+int sample_common(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *states_inout, double *energies_out,
+                  int32_t num_betas, const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds,
+                  int32_t seed_mode, int32_t mode, qa_interrupt_fn interrupt, void *iuser, qa_stats *stats_out) {
+    if (!ctx || !M) return fail(QA_ERR_ARG, "null context or model");
+    if (M->ctx != ctx) return fail(QA_ERR_ARG, "model belongs to another context");
+    if (reads_per_problem < 0) return fail(QA_ERR_ARG, "negative num_reads");
+    if (mode != QA_MODE_REFERENCE) return fail(QA_ERR_ARG, "unknown mode");
+    if (seed_mode != QA_SEED_PER_READ && seed_mode != QA_SEED_STREAM) return fail(QA_ERR_ARG, "unknown seed_mode");
+    if (seed_mode == QA_SEED_STREAM && M->num_problems != 1) return fail(QA_ERR_ARG, "stream seeding needs a single problem");
+    int rc = check_schedule(num_betas, beta_schedule, sweeps_per_beta);
+    if (rc) return rc;
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const int64_t total_reads = (int64_t)M->num_problems * reads_per_problem;
+    qa_stats st;
+    memset(&st, 0, sizeof(st));
+    const uint32_t launches0 = ctx->launches;
+    if (total_reads == 0) {
+        if (stats_out) *stats_out = st;
+        return 0;
+    }
+    if (!states_inout || !energies_out || !seeds) return fail(QA_ERR_ARG, "null states/energies/seeds");
+    const int64_t state_bytes = (int64_t)reads_per_problem * M->n_total;
+
+    QA_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int8_t *d_states = states_inout;
+    const bool st_host = !is_device_ptr(states_inout);
+    if (st_host) {
+        rc = ensure(ctx->states, (size_t)std::max<int64_t>(state_bytes, 1));
+        if (rc) return rc;
+        d_states = (int8_t *)ctx->states.p;
+        QA_CUDA(cudaMemcpyAsync(d_states, states_inout, (size_t)state_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    double *d_energies = energies_out;
+    const bool en_host = !is_device_ptr(energies_out);
+    if (en_host) {
+        rc = ensure(ctx->energies, (size_t)total_reads * sizeof(double));
+        if (rc) return rc;
+        d_energies = (double *)ctx->energies.p;
+    }
+    const int64_t nseeds = seed_mode == QA_SEED_STREAM ? 1 : total_reads;
+    const unsigned long long *d_seeds = (const unsigned long long *)seeds;
+    if (!is_device_ptr(seeds)) {
+        rc = ensure(ctx->seeds, (size_t)nseeds * sizeof(uint64_t));
+        if (rc) return rc;
+        QA_CUDA(cudaMemcpyAsync(ctx->seeds.p, seeds, (size_t)nseeds * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        d_seeds = (const unsigned long long *)ctx->seeds.p;
+    }
+    const double *d_betas = beta_schedule;
+    if (num_betas > 0 && !is_device_ptr(beta_schedule)) {
+        rc = ensure(ctx->betas, (size_t)num_betas * sizeof(double));
+        if (rc) return rc;
+        QA_CUDA(cudaMemcpyAsync(ctx->betas.p, beta_schedule, (size_t)num_betas * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        d_betas = (const double *)ctx->betas.p;
+    }
+    QA_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    int64_t completed = 0;
+    rc = run_anneal(ctx, M, reads_per_problem, d_states, d_energies, num_betas, d_betas, sweeps_per_beta, d_seeds, seed_mode,
+                    interrupt, iuser, &st, &completed);
+    if (rc) return rc;
+
+    QA_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (st_host) QA_CUDA(cudaMemcpyAsync(states_inout, d_states, (size_t)state_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (en_host) QA_CUDA(cudaMemcpyAsync(energies_out, d_energies, (size_t)total_reads * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    st.ms_h2d += elapsed(ctx->ev[0], ctx->ev[1]);
+    st.ms_d2h += elapsed(ctx->ev[4], ctx->ev[5]);
+    st.total_launches = ctx->launches - launches0;
+    if (stats_out) *stats_out = st;
+    return (int)std::min<int64_t>(completed / M->num_problems, 0x7fffffff);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *qa_last_error(void) { return g_err.c_str(); }
+
+int qa_version(void) { return QA_VERSION; }
+
+int qa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int qa_ctx_create(int device_id, qa_ctx **out) {
+    if (!out) return fail(QA_ERR_ARG, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(QA_ERR_CUDA, "no CUDA device available: libqanneal has no CPU fallback");
+    }
+    if (device_id < 0 || device_id >= ndev) return fail(QA_ERR_ARG, "device_id out of range");
+    QA_CUDA(cudaSetDevice(device_id));
+    qa_ctx *ctx = new qa_ctx();
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    QA_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    ctx->num_sms = prop.multiProcessorCount;
+    QA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) QA_CUDA(cudaEventCreate(&ev));
+    QA_CUDA(cudaMalloc((void **)&ctx->d_stats, (QA_NSTAT + 1) * sizeof(unsigned long long)));
+    QA_CUDA(cudaMalloc((void **)&ctx->d_flag, 2 * sizeof(int)));
+    QA_CUDA(cudaMalloc((void **)&ctx->d_best_e, sizeof(double)));
+    QA_CUDA(cudaMalloc((void **)&ctx->d_best_i, sizeof(long long)));
+    *out = ctx;
+    return QA_OK;
+}
+
+int qa_ctx_destroy(qa_ctx *ctx) {
+    if (!ctx) return QA_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    release(ctx->f); release(ctx->spw); release(ctx->states); release(ctx->energies); release(ctx->seeds);
+    release(ctx->betas); release(ctx->packed); release(ctx->misc); release(ctx->cubtmp);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->d_best_e) cudaFree(ctx->d_best_e);
+    if (ctx->d_best_i) cudaFree(ctx->d_best_i);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return QA_OK;
+}
+
+int qa_ctx_synchronize(qa_ctx *ctx) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_ctx_resident_reads(qa_ctx *ctx) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    int bps = 0;
+    QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<false>, QA_TPB_MAX, 0));
+    return bps * ctx->num_sms * (QA_TPB_MAX / 32);
+}
+
+int qa_model_from_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const int32_t *starts, const int32_t *ends,
+                        const double *weights, qa_model **out) {
+    if (!ctx || !out) return fail(QA_ERR_ARG, "null context or out");
+    *out = nullptr;
+    if (n < 0 || m < 0) return fail(QA_ERR_ARG, "negative size");
+    if ((n > 0 && !h) || (m > 0 && (!starts || !ends || !weights))) return fail(QA_ERR_ARG, "null model vector");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const int64_t voff[2] = {0, n}, coff[2] = {0, m};
+    return model_create(ctx, 1, voff, coff, h, starts, ends, weights, out);
+}
+
+int qa_model_set_groups(qa_model *M, int32_t ngroups, const int32_t *grp, const int32_t *coef, const double *lambda,
+                        const int64_t *kappa) {
+    if (!M) return fail(QA_ERR_ARG, "null model");
+    if (M->num_problems != 1) return fail(QA_ERR_ARG, "groups need a single-problem model");
+    if (ngroups < 0 || ngroups > QA_MAX_GROUPS) return fail(QA_ERR_LIMIT, "ngroups must be in [0, QA_MAX_GROUPS]");
+    qa_ctx *ctx = M->ctx;
+    QA_CUDA(cudaSetDevice(ctx->device));
+    if (M->grp) { cudaFree(M->grp); M->grp = nullptr; }
+    if (M->coef) { cudaFree(M->coef); M->coef = nullptr; }
+    if (M->lambda) { cudaFree(M->lambda); M->lambda = nullptr; }
+    if (M->kappa) { cudaFree(M->kappa); M->kappa = nullptr; }
+    M->ngroups = ngroups;
+    ProblemDesc &D = M->descs[0];
+    D.ngroups = ngroups;
+    D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
+    if (ngroups == 0) return QA_OK;
+    if (!grp || !coef || !lambda || !kappa) return fail(QA_ERR_ARG, "null group vector");
+    const int32_t n = D.n;
+    const int64_t npad = (int64_t)D.nch * 32;
+    // host-side validation: exact integer arithmetic must stay below 2^53 (and (M+kappa)^2 below 2^62)
+    std::vector<int32_t> hg(npad, -1), hc(npad, 0);
+    std::vector<int32_t> tg(n), tc(n);
+    QA_CUDA(cudaMemcpy(tg.data(), grp, (size_t)n * sizeof(int32_t), cudaMemcpyDefault));
+    QA_CUDA(cudaMemcpy(tc.data(), coef, (size_t)n * sizeof(int32_t), cudaMemcpyDefault));
+    std::vector<int64_t> hk(ngroups);
+    QA_CUDA(cudaMemcpy(hk.data(), kappa, (size_t)ngroups * sizeof(int64_t), cudaMemcpyDefault));
+    std::vector<double> sumabs(ngroups, 0.0), maxa(ngroups, 0.0);
+    for (int v = 0; v < n; ++v) {
+        if (tg[v] >= ngroups) return fail(QA_ERR_ARG, "group index out of range");
+        hg[v] = tg[v] < 0 ? -1 : tg[v];
+        hc[v] = tc[v];
+        if (tg[v] >= 0) {
+            sumabs[tg[v]] += std::fabs((double)tc[v]);
+            maxa[tg[v]] = std::max(maxa[tg[v]], std::fabs((double)tc[v]));
+        }
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        const double span = sumabs[g] + std::fabs((double)hk[g]);
+        if (span >= 2147483648.0 || maxa[g] * (maxa[g] + span) >= 9007199254740992.0)
+            return fail(QA_ERR_LIMIT, "group coefficients too large for exact integer evaluation");
+    }
+    QA_CUDA(cudaMalloc((void **)&M->grp, npad * sizeof(int32_t)));
+    QA_CUDA(cudaMalloc((void **)&M->coef, npad * sizeof(int32_t)));
+    QA_CUDA(cudaMalloc((void **)&M->lambda, ngroups * sizeof(double)));
+    QA_CUDA(cudaMalloc((void **)&M->kappa, ngroups * sizeof(long long)));
+    QA_CUDA(cudaMemcpy(M->grp, hg.data(), npad * sizeof(int32_t), cudaMemcpyHostToDevice));
+    QA_CUDA(cudaMemcpy(M->coef, hc.data(), npad * sizeof(int32_t), cudaMemcpyHostToDevice));
+    QA_CUDA(cudaMemcpy(M->lambda, lambda, ngroups * sizeof(double), cudaMemcpyDefault));
+    QA_CUDA(cudaMemcpy(M->kappa, hk.data(), ngroups * sizeof(long long), cudaMemcpyHostToDevice));
+    D.grp = M->grp; D.coef = M->coef; D.lambda = M->lambda; D.kappa = M->kappa;
+    return QA_OK;
+}
+
+int qa_model_num_variables(const qa_model *M) { return M ? (int)M->n_total : fail(QA_ERR_ARG, "null model"); }
+int64_t qa_model_num_couplers(const qa_model *M) { return M ? M->m_total : (int64_t)fail(QA_ERR_ARG, "null model"); }
+int qa_model_max_degree(const qa_model *M) { return M ? M->max_deg : fail(QA_ERR_ARG, "null model"); }
+
+int qa_model_get_ising(const qa_model *M, double *h, int32_t *starts, int32_t *ends, double *weights) {
+    if (!M) return fail(QA_ERR_ARG, "null model");
+    QA_CUDA(cudaSetDevice(M->ctx->device));
+    if (h) QA_CUDA(cudaMemcpy(h, M->h, (size_t)M->n_total * sizeof(double), cudaMemcpyDefault));
+    if (starts) QA_CUDA(cudaMemcpy(starts, M->starts, (size_t)M->m_total * sizeof(int32_t), cudaMemcpyDefault));
+    if (ends) QA_CUDA(cudaMemcpy(ends, M->ends, (size_t)M->m_total * sizeof(int32_t), cudaMemcpyDefault));
+    if (weights) QA_CUDA(cudaMemcpy(weights, M->w, (size_t)M->m_total * sizeof(double), cudaMemcpyDefault));
+    return QA_OK;
+}
+
+int qa_model_destroy(qa_model *M) {
+    if (!M) return QA_OK;
+    cudaSetDevice(M->ctx->device);
+    cudaStreamSynchronize(M->ctx->stream);
+    void *ptrs[] = {M->h, M->starts, M->ends, M->w, M->rowptr, M->col, M->val, M->grp, M->coef, M->lambda, M->kappa, M->d_descs};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete M;
+    return QA_OK;
+}
+
+int qa_sa_sample_model(qa_ctx *ctx, qa_model *model, int32_t num_reads, int8_t *states_inout, double *energies_out,
+                       int32_t num_betas, const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds,
+                       int32_t seed_mode, int32_t mode, qa_interrupt_fn interrupt, void *interrupt_user, qa_stats *stats_out) {
+    if (model && model->num_problems != 1) return fail(QA_ERR_ARG, "use qa_sa_sample_ising_batch for batched models");
+    return sample_common(ctx, model, num_reads, states_inout, energies_out, num_betas, beta_schedule, sweeps_per_beta, seeds,
+                         seed_mode, mode, interrupt, interrupt_user, stats_out);
+}
+
+int qa_sa_sample_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const int32_t *starts, const int32_t *ends,
+                       const double *weights, int32_t num_reads, int8_t *states_inout, double *energies_out, int32_t num_betas,
+                       const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds, int32_t seed_mode,
+                       int32_t mode, qa_stats *stats_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    cudaEvent_t b0 = nullptr, b1 = nullptr;
+    QA_CUDA(cudaSetDevice(ctx->device));
+    QA_CUDA(cudaEventCreate(&b0));
+    QA_CUDA(cudaEventCreate(&b1));
+    const uint32_t l0 = ctx->launches;
+    cudaEventRecord(b0, ctx->stream);
+    qa_model *M = nullptr;
+    int rc = qa_model_from_ising(ctx, n, h, m, starts, ends, weights, &M);
+    cudaEventRecord(b1, ctx->stream);
+    if (rc == QA_OK) {
+        rc = sample_common(ctx, M, num_reads, states_inout, energies_out, num_betas, beta_schedule, sweeps_per_beta, seeds,
+                           seed_mode, mode, nullptr, nullptr, stats_out);
+        if (rc >= 0 && stats_out) {
+            cudaEventSynchronize(b1);
+            stats_out->ms_build = elapsed(b0, b1);
+            stats_out->total_launches = ctx->launches - l0;
+        }
+    }
+    qa_model_destroy(M);
+    cudaEventDestroy(b0);
+    cudaEventDestroy(b1);
+    return rc;
+}
+
+int qa_sa_sample_ising_batch(qa_ctx *ctx, int32_t num_problems, const int64_t *var_offsets, const int64_t *coupler_offsets,
+                             const double *h, const int32_t *starts, const int32_t *ends, const double *weights,
+                             int32_t reads_per_problem, int8_t *states_inout, double *energies_out, int32_t num_betas,
+                             const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds, qa_stats *stats_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (num_problems < 1 || !var_offsets || !coupler_offsets) return fail(QA_ERR_ARG, "bad batch description");
+    for (int p = 0; p < num_problems; ++p)
+        if (var_offsets[p + 1] < var_offsets[p] || coupler_offsets[p + 1] < coupler_offsets[p])
+            return fail(QA_ERR_ARG, "offsets must be non-decreasing");
+    if (var_offsets[0] != 0 || coupler_offsets[0] != 0) return fail(QA_ERR_ARG, "offsets must start at 0");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    cudaEvent_t b0 = nullptr, b1 = nullptr;
+    QA_CUDA(cudaEventCreate(&b0));
+    QA_CUDA(cudaEventCreate(&b1));
+    const uint32_t l0 = ctx->launches;
+    cudaEventRecord(b0, ctx->stream);
+    qa_model *M = nullptr;
+    int rc = model_create(ctx, num_problems, var_offsets, coupler_offsets, h, starts, ends, weights, &M);
+    cudaEventRecord(b1, ctx->stream);
+    if (rc == QA_OK) {
+        rc = sample_common(ctx, M, reads_per_problem, states_inout, energies_out, num_betas, beta_schedule, sweeps_per_beta,
+                           seeds, QA_SEED_PER_READ, QA_MODE_REFERENCE, nullptr, nullptr, stats_out);
+        if (rc >= 0 && stats_out) {
+            cudaEventSynchronize(b1);
+            stats_out->ms_build = elapsed(b0, b1);
+            stats_out->total_launches = ctx->launches - l0;
+        }
+    }
+    qa_model_destroy(M);
+    cudaEventDestroy(b0);
+    cudaEventDestroy(b1);
+    return rc;
+}
+
+int qa_energy_argmin(qa_ctx *ctx, qa_model *M, int32_t num_reads, const int8_t *states, double *energies_out,
+                     double *best_energy, int64_t *best_index, qa_stats *stats_out) {
+    if (!ctx || !M) return fail(QA_ERR_ARG, "null context or model");
+    if (M->num_problems != 1) return fail(QA_ERR_ARG, "single-problem model required");
+    if (num_reads < 0) return fail(QA_ERR_ARG, "negative num_reads");
+    qa_stats st;
+    memset(&st, 0, sizeof(st));
+    if (num_reads == 0) {
+        if (best_energy) *best_energy = INFINITY;
+        if (best_index) *best_index = -1;
+        if (stats_out) *stats_out = st;
+        return QA_OK;
+    }
+    if (!states) return fail(QA_ERR_ARG, "null states");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t l0 = ctx->launches;
+    ProblemDesc &D = M->descs[0];
+    const int32_t rpad = (num_reads + 31) & ~31;
+    const int64_t state_bytes = (int64_t)num_reads * D.n;
+    QA_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    const int8_t *d_states = states;
+    if (!is_device_ptr(states)) {
+        int rc = ensure(ctx->states, (size_t)std::max<int64_t>(state_bytes, 1));
+        if (rc) return rc;
+        QA_CUDA(cudaMemcpyAsync(ctx->states.p, states, (size_t)state_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_states = (const int8_t *)ctx->states.p;
+    }
+    double *d_energies = energies_out;
+    const bool en_host = !energies_out || !is_device_ptr(energies_out);
+    if (en_host) {
+        int rc = ensure(ctx->energies, (size_t)num_reads * sizeof(double));
+        if (rc) return rc;
+        d_energies = (double *)ctx->energies.p;
+    }
+    int rc = ensure(ctx->packed, (size_t)std::max<int64_t>((int64_t)D.nch * rpad, 1) * sizeof(uint32_t));
+    if (rc) return rc;
+    D.reads = num_reads;
+    D.rpad = rpad;
+    D.read_base = 0;
+    D.states = const_cast<int8_t *>(d_states);
+    D.packedT = (uint32_t *)ctx->packed.p;
+    D.energies = d_energies;
+    QA_CUDA(cudaMemcpyAsync(M->d_descs, &D, sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
+    QA_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    {
+        const int tpb = 256;
+        const int64_t threads = (int64_t)num_reads * 32;
+        k_pack_states<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(D, ctx->d_flag);
+        dim3 g((unsigned)((num_reads + 127) / 128), 1);
+        k_energy<<<g, 128, 0, ctx->stream>>>(M->d_descs);
+        k_argmin<<<1, 1024, 0, ctx->stream>>>(d_energies, num_reads, ctx->d_best_e, ctx->d_best_i);
+        QA_CUDA(cudaGetLastError());
+        ctx->launches += 3;
+    }
+    QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    int flag = 0;
+    double be = 0;
+    long long bi = 0;
+    QA_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(&be, ctx->d_best_e, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(&bi, ctx->d_best_i, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (energies_out && en_host)
+        QA_CUDA(cudaMemcpyAsync(energies_out, d_energies, (size_t)num_reads * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flag != 0) return fail(flag, "states must be +1/-1");
+    if (best_energy) *best_energy = be;
+    if (best_index) *best_index = bi;
+    st.ms_h2d = elapsed(ctx->ev[0], ctx->ev[1]);
+    st.ms_energy = elapsed(ctx->ev[1], ctx->ev[2]);
+    st.ms_d2h = elapsed(ctx->ev[2], ctx->ev[3]);
+    st.total_launches = ctx->launches - l0;
+    if (stats_out) *stats_out = st;
+    return QA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""Thin object layer over the C ABI (include/qanneal.h): ``Context`` (one GPU) and ``IsingModel``.
+
+Host buffers are numpy arrays; device buffers may be passed as torch CUDA tensors (used purely as
+memory) -- the library detects device pointers itself.  Nothing here computes: every number comes
+out of libqanneal.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import QAStats, check, ptr
+
+
+def _is_tensor(x) -> bool:
+    return hasattr(x, "data_ptr") and not isinstance(x, np.ndarray)
+
+
+def _as(x, dtype, name):
+    """numpy view with the dtype/contiguity the ABI expects (torch tensors are passed through)."""
+    if x is None or _is_tensor(x):
+        return x
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a
+
+
+class Context:
+    """One GPU + one CUDA stream + reusable scratch (``qa_ctx``)."""
+
+    def __init__(self, device: int = 0):
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.qa_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().qa_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def resident_reads(self) -> int:
+        return check(_lib.load().qa_ctx_resident_reads(self._h))
+
+    def synchronize(self):
+        check(_lib.load().qa_ctx_synchronize(self._h))
+
+    # -- neal's general_simulated_annealing, one shot, host or device buffers --------------------
+    def sample_ising(self, h, starts, ends, weights, states, beta_schedule, sweeps_per_beta, seeds,
+                     seed_mode=_lib.QA_SEED_PER_READ, mode=_lib.QA_MODE_REFERENCE, energies=None):
+        h = _as(h, np.float64, "h")
+        starts = _as(starts, np.int32, "starts")
+        ends = _as(ends, np.int32, "ends")
+        weights = _as(weights, np.float64, "weights")
+        beta_schedule = _as(beta_schedule, np.float64, "beta_schedule")
+        seeds = _as(seeds, np.uint64, "seeds")
+        n = int(h.shape[0])
+        m = int(starts.shape[0])
+        num_reads = int(states.shape[0]) if n else 0
+        if energies is None:
+            energies = np.empty(num_reads, dtype=np.float64)
+        st = QAStats()
+        done = check(_lib.load().qa_sa_sample_ising(
+            self._h, n, ptr(h), m, ptr(starts), ptr(ends), ptr(weights), num_reads, ptr(states), ptr(energies),
+            int(beta_schedule.shape[0]), ptr(beta_schedule), int(sweeps_per_beta), ptr(seeds), int(seed_mode), int(mode),
+            C.byref(st)))
+        return energies, st, done
+
+    def sample_ising_batch(self, var_offsets, coupler_offsets, h, starts, ends, weights, reads_per_problem, states,
+                           beta_schedule, sweeps_per_beta, seeds, energies=None):
+        var_offsets = np.ascontiguousarray(var_offsets, dtype=np.int64)
+        coupler_offsets = np.ascontiguousarray(coupler_offsets, dtype=np.int64)
+        h = _as(h, np.float64, "h")
+        starts = _as(starts, np.int32, "starts")
+        ends = _as(ends, np.int32, "ends")
+        weights = _as(weights, np.float64, "weights")
+        beta_schedule = _as(beta_schedule, np.float64, "beta_schedule")
+        seeds = _as(seeds, np.uint64, "seeds")
+        num_problems = int(var_offsets.shape[0]) - 1
+        if energies is None:
+            energies = np.empty(num_problems * int(reads_per_problem), dtype=np.float64)
+        st = QAStats()
+        done = check(_lib.load().qa_sa_sample_ising_batch(
+            self._h, num_problems, ptr(var_offsets), ptr(coupler_offsets), ptr(h), ptr(starts), ptr(ends), ptr(weights),
+            int(reads_per_problem), ptr(states), ptr(energies), int(beta_schedule.shape[0]), ptr(beta_schedule),
+            int(sweeps_per_beta), ptr(seeds), C.byref(st)))
+        return energies, st, done
+
+
+class IsingModel:
+    """A model resident on the GPU (``qa_model``): CSR adjacency in neal's push_back order + h."""
+
+    def __init__(self, ctx: Context, h, starts, ends, weights):
+        self.ctx = ctx
+        h = _as(h, np.float64, "h")
+        starts = _as(starts, np.int32, "starts")
+        ends = _as(ends, np.int32, "ends")
+        weights = _as(weights, np.float64, "weights")
+        hm = C.c_void_p()
+        check(_lib.load().qa_model_from_ising(ctx._h, int(h.shape[0]), ptr(h), int(starts.shape[0]), ptr(starts), ptr(ends),
+                                              ptr(weights), C.byref(hm)))
+        self._h = hm
+        self.num_variables = int(h.shape[0])
+        self.num_couplers = int(starts.shape[0])
+        self.num_groups = 0
+
+    @classmethod
+    def _from_handle(cls, ctx: Context, handle) -> "IsingModel":
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self._h = handle
+        lib = _lib.load()
+        self.num_variables = check(lib.qa_model_num_variables(handle))
+        self.num_couplers = int(lib.qa_model_num_couplers(handle))
+        self.num_groups = 0
+        return self
+
+    def set_groups(self, grp, coef, lam, kappa):
+        grp = np.ascontiguousarray(grp, dtype=np.int32)
+        coef = np.ascontiguousarray(coef, dtype=np.int32)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        kappa = np.ascontiguousarray(kappa, dtype=np.int64)
+        if grp.shape[0] != self.num_variables or coef.shape[0] != self.num_variables:
+            raise ValueError("grp/coef must have one entry per variable")
+        check(_lib.load().qa_model_set_groups(self._h, int(lam.shape[0]), ptr(grp), ptr(coef), ptr(lam), ptr(kappa)))
+        self.num_groups = int(lam.shape[0])
+
+    @property
+    def max_degree(self) -> int:
+        return check(_lib.load().qa_model_max_degree(self._h))
+
+    def get_ising(self):
+        h = np.empty(self.num_variables, dtype=np.float64)
+        s = np.empty(self.num_couplers, dtype=np.int32)
+        e = np.empty(self.num_couplers, dtype=np.int32)
+        w = np.empty(self.num_couplers, dtype=np.float64)
+        check(_lib.load().qa_model_get_ising(self._h, ptr(h), ptr(s), ptr(e), ptr(w)))
+        return h, s, e, w
+
+    def sample(self, states, beta_schedule, sweeps_per_beta, seeds, seed_mode=_lib.QA_SEED_PER_READ,
+               mode=_lib.QA_MODE_REFERENCE, energies=None, interrupt_function=None):
+        """Anneal ``states`` ([R][n] int8 +-1, in/out).  Returns (energies, QAStats, reads_completed)."""
+        beta_schedule = _as(beta_schedule, np.float64, "beta_schedule")
+        seeds = _as(seeds, np.uint64, "seeds")
+        num_reads = int(states.shape[0])
+        if not _is_tensor(states):
+            if states.dtype != np.int8 or not states.flags.c_contiguous:
+                raise ValueError("states must be a C-contiguous int8 array (it is updated in place)")
+        if energies is None:
+            energies = np.empty(num_reads, dtype=np.float64)
+        cb = None
+        if interrupt_function is not None:
+            cb = _lib.INTERRUPT_FN(lambda _u: 1 if interrupt_function() else 0)
+        st = QAStats()
+        done = check(_lib.load().qa_sa_sample_model(
+            self.ctx._h, self._h, num_reads, ptr(states), ptr(energies), int(beta_schedule.shape[0]), ptr(beta_schedule),
+            int(sweeps_per_beta), ptr(seeds), int(seed_mode), int(mode),
+            C.cast(cb, C.c_void_p) if cb is not None else None, None, C.byref(st)))
+        return energies, st, done
+
+    def energies(self, states, energies=None):
+        """neal get_state_energy of each row + (best_energy, best_index) by the warp-shuffle argmin kernel."""
+        num_reads = int(states.shape[0])
+        if not _is_tensor(states):
+            states = np.ascontiguousarray(states, dtype=np.int8)
+        if energies is None:
+            energies = np.empty(num_reads, dtype=np.float64)
+        be = C.c_double()
+        bi = C.c_int64()
+        st = QAStats()
+        check(_lib.load().qa_energy_argmin(self.ctx._h, self._h, num_reads, ptr(states), ptr(energies), C.byref(be),
+                                           C.byref(bi), C.byref(st)))
+        return energies, float(be.value), int(bi.value), st
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().qa_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

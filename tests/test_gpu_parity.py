@@ -1,0 +1,208 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: reference-order mode is BIT-EXACT -- final states bytewise, energies bitwise (uint64 view) -- for every model
+family of the reference and for the edge cases of the domain (ragged sizes, dense rows, isolated
+variables, stream seeding, batches).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from scrna_seq_qannealing_clustering_b200 import _lib, models, schedule, snn
+from scrna_seq_qannealing_clustering_b200.engine import IsingModel
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(ctx, model, R, sweeps, seed, beta_range=(0.05, 8.0), seed_mode=0, spb=1):
+    n = model.num_variables
+    groups = model.groups.astuple() if model.groups is not None else None
+    betas, spb = schedule.make_beta_schedule(beta_range, sweeps, spb, "geometric")
+    seeds = schedule.per_read_seeds(seed, R) if seed_mode == 0 else np.array([seed], dtype=np.uint64)
+    init = schedule.random_spin_states(R, n, seed)
+    ref_states = init.copy()
+    ref_e, ref_st = oracle.sample_ising(model.h, model.starts, model.ends, model.weights, ref_states, betas, spb, seeds,
+                                        seed_mode=seed_mode, groups=groups)
+    gm = IsingModel(ctx, model.h, model.starts, model.ends, model.weights)
+    if groups is not None:
+        gm.set_groups(*groups)
+    states = init.copy()
+    e, st, done = gm.sample(states, betas, spb, seeds, seed_mode=seed_mode)
+    gm.close()
+    assert done == R
+    return states, e, st, ref_states, ref_e, ref_st
+
+
+def _assert_bit_exact(states, e, st, ref_states, ref_e, ref_st):
+    assert np.array_equal(states, ref_states)
+    assert np.array_equal(e.view(np.uint64), ref_e.view(np.uint64))
+    for key in ("attempts", "candidates", "draws", "accepted", "nbr_updates"):
+        assert getattr(st, key) == ref_st[key], key
+
+
+@pytest.fixture(scope="module")
+def graph256():
+    return snn.synthetic_snn(256, k=5, seed=3)[0]
+
+
+def test_subsampling_sparse(gpu_ctx, graph256):
+    _assert_bit_exact(*_run_both(gpu_ctx, models.subsampling_model(graph256, 7.0), 200, 100, 5))
+
+
+def test_cut_linear(gpu_ctx, graph256):
+    _assert_bit_exact(*_run_both(gpu_ctx, models.cut_linear_model(graph256, 0.01, 1.0), 100, 100, 6))
+
+
+def test_cut_balance_materialised_dense_rows(gpu_ctx, graph256):
+    m = models.cut_balance_model(graph256, 0.05, structured=False)  # K_256: every row has 255 neighbours
+    _assert_bit_exact(*_run_both(gpu_ctx, m, 64, 60, 7, beta_range=(0.01, 4.0)))
+
+
+def test_cut_balance_structured_group(gpu_ctx, graph256):
+    m = models.cut_balance_model(graph256, 0.05, structured=True)
+    _assert_bit_exact(*_run_both(gpu_ctx, m, 100, 100, 8, beta_range=(0.01, 4.0)))
+
+
+@pytest.mark.parametrize("semantics", ["as_written", "intended"])
+def test_dqm_structured(gpu_ctx, graph256, semantics):
+    m = models.dqm_model(graph256, 4, 0.005, semantics=semantics)
+    _assert_bit_exact(*_run_both(gpu_ctx, m, 64, 80, 9, beta_range=(0.02, 6.0)))
+
+
+def test_cqm_structured_with_slack(gpu_ctx, graph256):
+    m = models.cqm_model(graph256, 4, min_size=20)
+    _assert_bit_exact(*_run_both(gpu_ctx, m, 64, 80, 10, beta_range=(0.02, 6.0)))
+
+
+def test_cqm_materialised_equals_structured_energy(gpu_ctx):
+    g = snn.synthetic_snn(48, k=4, seed=2)[0]
+    m = models.cqm_model(g, 3, min_size=5)
+    states, e, *_ = _run_both(gpu_ctx, m, 32, 50, 11)
+    dense = m.materialise()
+    e_dense = dense.energies(states)
+    assert np.allclose(e + m.offset, e_dense, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 95, 1000])
+def test_ragged_sizes(gpu_ctx, n):
+    rng = np.random.default_rng(n)
+    m_edges = min(n * (n - 1) // 2, 3 * n)
+    pairs = set()
+    while len(pairs) < m_edges:
+        u, v = rng.integers(0, n, 2)
+        if u != v:
+            pairs.add((max(u, v), min(u, v)))
+    pairs = sorted(pairs)
+    starts = np.array([p[0] for p in pairs], dtype=np.int32)
+    ends = np.array([p[1] for p in pairs], dtype=np.int32)
+    model = models.LoweredModel(rng.normal(size=n), starts, ends, rng.normal(size=len(pairs)), 0.0, list(range(n)))
+    _assert_bit_exact(*_run_both(gpu_ctx, model, 37, 40, n, beta_range=(0.1, 5.0)))
+
+
+def test_unsorted_coupler_order_and_isolated_variables(gpu_ctx):
+    """neal's adjacency is push_back order, not sorted: shuffle the couplers and the result must still match."""
+    rng = np.random.default_rng(0)
+    n = 70
+    pairs = [(u, v) for u in range(60) for v in range(u) if rng.random() < 0.2]  # variables 60..69 isolated
+    rng.shuffle(pairs)
+    flip = rng.random(len(pairs)) < 0.5
+    starts = np.array([p[1] if f else p[0] for p, f in zip(pairs, flip)], dtype=np.int32)
+    ends = np.array([p[0] if f else p[1] for p, f in zip(pairs, flip)], dtype=np.int32)
+    model = models.LoweredModel(rng.normal(size=n), starts, ends, rng.normal(size=len(pairs)), 0.0, list(range(n)))
+    _assert_bit_exact(*_run_both(gpu_ctx, model, 50, 60, 3, beta_range=(0.1, 5.0)))
+
+
+def test_stream_seeding_matches_neal_multi_read_call(gpu_ctx, graph256):
+    m = models.subsampling_model(graph256, 7.0)
+    _assert_bit_exact(*_run_both(gpu_ctx, m, 12, 50, 1234, seed_mode=1))
+
+
+def test_seed_zero_and_sweeps_per_beta(gpu_ctx, graph256):
+    m = models.subsampling_model(graph256, 7.0)
+    _assert_bit_exact(*_run_both(gpu_ctx, m, 8, 60, 0, seed_mode=1, spb=3))
+
+
+def test_many_reads_more_than_resident(gpu_ctx):
+    g = snn.synthetic_snn(64, k=4, seed=5)[0]
+    m = models.subsampling_model(g, 7.0)
+    R = gpu_ctx.resident_reads + 777
+    _assert_bit_exact(*_run_both(gpu_ctx, m, R, 20, 21, beta_range=(0.1, 5.0)))
+
+
+def test_batch_of_independent_problems(gpu_ctx):
+    graphs = snn.subsample_problems(2000, 5, 200, k=6, dim=10, seed=4)
+    ms = [models.subsampling_model(g, 7.0) for g in graphs]
+    rpp = 20
+    betas, spb = schedule.make_beta_schedule((0.05, 6.0), 50, 1, "geometric")
+    voff = np.cumsum([0] + [m.num_variables for m in ms])
+    coff = np.cumsum([0] + [m.num_couplers for m in ms])
+    seeds = schedule.per_read_seeds(17, rpp * len(ms))
+    inits = [schedule.random_spin_states(rpp, m.num_variables, 100 + i) for i, m in enumerate(ms)]
+    states = np.concatenate([s.ravel() for s in inits]).copy()
+    e, st, done = gpu_ctx.sample_ising_batch(voff, coff, np.concatenate([m.h for m in ms]),
+                                             np.concatenate([m.starts for m in ms]), np.concatenate([m.ends for m in ms]),
+                                             np.concatenate([m.weights for m in ms]), rpp, states, betas, spb, seeds)
+    assert done == rpp
+    off = 0
+    for i, m in enumerate(ms):
+        ref = inits[i].copy()
+        ref_e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, ref, betas, spb, seeds[i * rpp:(i + 1) * rpp])
+        got = states[off:off + rpp * m.num_variables].reshape(rpp, m.num_variables)
+        off += rpp * m.num_variables
+        assert np.array_equal(got, ref)
+        assert np.array_equal(e[i * rpp:(i + 1) * rpp].view(np.uint64), ref_e.view(np.uint64))
+
+
+def test_one_shot_host_buffers_like_neal(gpu_ctx, graph256):
+    m = models.subsampling_model(graph256, 7.0)
+    betas, spb = schedule.make_beta_schedule((0.05, 6.0), 50, 1, "geometric")
+    seeds = schedule.per_read_seeds(2, 40)
+    init = schedule.random_spin_states(40, m.num_variables, 2)
+    ref = init.copy()
+    ref_e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, ref, betas, spb, seeds)
+    states = init.copy()
+    e, st, done = gpu_ctx.sample_ising(m.h, m.starts, m.ends, m.weights, states, betas, spb, seeds)
+    assert done == 40 and np.array_equal(states, ref) and np.array_equal(e.view(np.uint64), ref_e.view(np.uint64))
+    assert st.total_launches >= 3 and st.ms_anneal > 0
+
+
+def test_energy_argmin_kernel(gpu_ctx, graph256):
+    m = models.cqm_model(graph256, 4, min_size=20)
+    groups = m.groups.astuple()
+    states = schedule.random_spin_states(1000, m.num_variables, 9)
+    ref = oracle.state_energies(m.h, m.starts, m.ends, m.weights, states, groups=groups)
+    gm = IsingModel(gpu_ctx, m.h, m.starts, m.ends, m.weights)
+    gm.set_groups(*groups)
+    e, be, bi, _ = gm.energies(states)
+    gm.close()
+    assert np.array_equal(e.view(np.uint64), ref.view(np.uint64))
+    assert bi == int(np.argmin(ref)) and be == ref.min()
+    # the QUBO-form value (dimod bqm.energies) agrees to 1e-12 relative
+    assert np.allclose(e + m.offset, m.energies(states), rtol=1e-12, atol=1e-9)
+
+
+def test_zero_sweeps_returns_initial_state_energies(gpu_ctx, graph256):
+    m = models.subsampling_model(graph256, 7.0)
+    init = schedule.random_spin_states(5, m.num_variables, 1)
+    gm = IsingModel(gpu_ctx, m.h, m.starts, m.ends, m.weights)
+    states = init.copy()
+    e, st, done = gm.sample(states, np.zeros(0), 1, schedule.per_read_seeds(1, 5))
+    gm.close()
+    assert np.array_equal(states, init)
+    assert np.array_equal(e.view(np.uint64), oracle.state_energies(m.h, m.starts, m.ends, m.weights, init).view(np.uint64))
+
+
+def test_error_codes(gpu_ctx):
+    h = np.zeros(4)
+    with pytest.raises(_lib.QAnnealError) as ei:
+        IsingModel(gpu_ctx, h, np.array([5], dtype=np.int32), np.array([0], dtype=np.int32), np.ones(1))
+    assert ei.value.code == -2
+    with pytest.raises(_lib.QAnnealError) as ei:
+        IsingModel(gpu_ctx, h, np.array([1], dtype=np.int32), np.array([1], dtype=np.int32), np.ones(1))
+    assert ei.value.code == -2
+    gm = IsingModel(gpu_ctx, h, np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.ones(1))
+    bad = np.zeros((2, 4), dtype=np.int8)
+    with pytest.raises(_lib.QAnnealError) as ei:
+        gm.sample(bad, np.array([1.0]), 1, schedule.per_read_seeds(0, 2))
+    assert ei.value.code == -3
+    gm.close()
