@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- spin-flip attempts/sec of the annealing hot path on BASELINE.json's config 3.
+
+Workload ("config.workload"): 8-way CQM-style clustering lowered to penalties on a 16 384-cell synthetic SNN graph
+(131 072 cell variables + 112 slack bits), neal-order Metropolis, 1000 sweeps, geometric beta schedule.  A "step" is
+one pass of the hot path over one batch of reads (``--reads`` per GPU): annealing kernel + energy kernel (+ the
+per-rank best gather at N > 1).  Reads shard over ranks with no data-path collective -> weak scaling.
+
+    value  whole-job attempts/s with model, states, seeds and schedule already resident in HBM
+    e2e    the same through the neal-shaped C-ABI call qa_sa_sample_ising with HOST (pinned) buffers: model vectors
+           and initial states copied in, adjacency built on the device, final states and energies copied out
+    roofline  algorithmic bytes of the annealing kernel / its CUDA-event duration / measured HBM copy bandwidth
+    cpu_baseline  the CPU oracle (restatement of neal's loop, oracle/) on a bounded sample of the same workload
+
+``--impl reference`` times the oracle alone, with all host threads, on bounded samples of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "spin_flip_attempts_per_sec"
+UNIT = "attempts/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=16384)
+    ap.add_argument("--clusters", type=int, default=8)
+    ap.add_argument("--reads", type=int, default=1184, help="reads per GPU per step (multiple of the 148 SMs)")
+    ap.add_argument("--sweeps", type=int, default=1000)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (0: 2 x host threads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_workload(args):
+    from scrna_seq_qannealing_clustering_b200 import models, schedule, snn
+    graph, _ = snn.synthetic_snn(args.cells, k=5, dim=15, centres=args.clusters, seed=0)
+    model = models.cqm_model(graph, args.clusters, min_size=20)
+    # beta range from the explicit couplers (one-hot + objective), not from the rank-1 size penalty: neal's default on
+    # the penalty would start at beta ~ 1e-8 and spend most sweeps at ~100 % acceptance (SURVEY.md hard part 4)
+    beta_range = schedule.default_ising_beta_range(model.h, model.starts, model.ends, model.weights, None)
+    betas, spb = schedule.make_beta_schedule(beta_range, args.sweeps, 1, "geometric")
+    return model, beta_range, betas, spb
+
+
+def workload_config(args, model, beta_range):
+    return {
+        "workload": f"config3: {args.clusters}-way CQM lowered to penalties, {args.cells}-cell synthetic SNN (k=5, trim 15), "
+                    f"{model.num_variables} vars, {model.num_couplers} couplers + {args.clusters} rank-1 size groups",
+        "reads_per_gpu_per_step": args.reads,
+        "num_sweeps": args.sweeps,
+        "beta_range": [float(beta_range[0]), float(beta_range[1])],
+        "beta_schedule_type": "geometric",
+        "onehot_penalty": model.meta["onehot_penalty"],
+        "size_penalty": model.meta["size_penalty"],
+        "mode": "reference-order (bit-exact vs oracle), per-read seeds",
+        "l2_policy": "per-step state (reads x n x 8 B of local fields) exceeds the 126 MB L2",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def algorithmic_bytes(stats: dict) -> float:
+    """Bytes the reference-order kernel must move (kernel K-ref):
+    8 B local field + 1 bit spin per attempt, 8 B fp64 reduction per neighbour update, 12 B CSR entry per neighbour of
+    an accepted flip, 8 B row pointers per chunk that had a candidate."""
+    return (8.125 * stats["attempts"] + 8.0 * stats["nbr_updates"] + 12.0 * stats["nbr_updates"] + 8.0 * stats["active_chunks"])
+
+
+def survey_bytes(stats: dict) -> float:
+    """SURVEY.md 8(d) formula for the reference (neal) layout: 8*N_att + 9*N_acc + 17*D_acc + 12*D_row."""
+    return 8.0 * stats["attempts"] + 9.0 * stats["accepted"] + 17.0 * stats["nbr_updates"] + 12.0 * stats["nbr_updates"]
+
+
+def run_cpu_sample(model, betas, spb, seed, reads, threads):
+    from oracle import oracle
+    from scrna_seq_qannealing_clustering_b200 import schedule
+    states = schedule.random_spin_states(reads, model.num_variables, seed)
+    seeds = schedule.per_read_seeds(seed, reads)
+    t0 = time.perf_counter()
+    e, st = oracle.sample_ising(model.h, model.starts, model.ends, model.weights, states, betas, spb, seeds,
+                                groups=model.groups.astuple() if model.groups is not None else None, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return st["attempts"] / dt, dt, float(e.min() + model.offset)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    model, beta_range, betas, spb = build_workload(args)
+    threads = oracle.num_threads()
+    reads = args.cpu_reads or threads
+    for _ in range(max(0, min(args.warmup, 1))):
+        run_cpu_sample(model, betas[: max(1, len(betas) // 50)], spb, args.seed, threads, threads)
+    rates, times = [], []
+    for s in range(args.steps):
+        r, dt, _ = run_cpu_sample(model, betas, spb, args.seed + s, reads, threads)
+        rates.append(r)
+        times.append(dt)
+    total_attempts = model.num_variables * len(betas) * spb * reads * args.steps
+    value = total_attempts / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, model, beta_range),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{reads} reads x {len(betas) * spb} sweeps x {model.num_variables} vars per step, OpenMP over reads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from scrna_seq_qannealing_clustering_b200 import _lib, schedule
+    from scrna_seq_qannealing_clustering_b200.engine import Context, IsingModel
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    model, beta_range, betas, spb = build_workload(args)
+    n = model.num_variables
+    R = args.reads
+    groups = model.groups.astuple()
+    first_read = rank * R
+    seeds = schedule.per_read_seeds(args.seed, R, first_read=first_read)
+    rng = np.random.default_rng(args.seed + 7919 * rank)
+    init_host = torch.from_numpy((rng.integers(0, 2, size=(R, n), dtype=np.int8) * 2 - 1).astype(np.int8)).pin_memory()
+
+    ctx = Context(local_rank)
+    gm = IsingModel(ctx, model.h, model.starts, model.ends, model.weights)
+    gm.set_groups(*groups)
+
+    # device-resident inputs (torch tensors used purely as HBM buffers)
+    init_dev = init_host.to(dev, non_blocking=False)
+    states_dev = torch.empty_like(init_dev)
+    energies_dev = torch.empty(R, dtype=torch.float64, device=dev)
+    seeds_dev = torch.from_numpy(seeds.view(np.int64)).to(dev)
+    betas_dev = torch.from_numpy(betas).to(dev)
+    best_buf = torch.zeros(2, dtype=torch.float64, device=dev)
+    gathered = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+
+    stats_acc = {}
+
+    def step_resident(record: bool):
+        states_dev.copy_(init_dev)
+        torch.cuda.synchronize()
+        e, st, done = gm.sample(states_dev, betas_dev, spb, seeds_dev, energies=energies_dev)
+        assert done == R
+        if world > 1:  # the path's only exchange: per-rank best (energy, global read index)
+            be, bi = torch.min(energies_dev, dim=0)
+            best_buf[0] = be
+            best_buf[1] = (first_read + bi).to(torch.float64)
+            dist.all_gather(gathered, best_buf)
+        if record:
+            for k, v in st.as_dict().items():
+                stats_acc[k] = stats_acc.get(k, 0) + v
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_resident(True)
+        barrier()
+        elapsed = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    attempts_per_step_per_gpu = n * len(betas) * spb * R
+    value = attempts_per_step_per_gpu * world * args.steps / elapsed
+
+    # ---- e2e: HOST buffers through the neal-shaped C-ABI entry point, copies inside the timed region -----------------
+    e2e = None
+    if not args.no_e2e:
+        host_states = torch.empty_like(init_host).pin_memory()
+        host_energies = torch.empty(R, dtype=torch.float64).pin_memory()
+        hs, he = host_states.numpy(), host_energies.numpy()
+
+        def step_e2e_groups():
+            hs[:] = init_host.numpy()
+            m2 = IsingModel(ctx, model.h, model.starts, model.ends, model.weights)
+            m2.set_groups(*groups)
+            _, st, done = m2.sample(hs, betas, spb, seeds, energies=he)
+            m2.close()
+            assert done == R
+            return st
+
+        e2e_steps = max(1, min(args.steps, 2))
+        step_e2e_groups()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            st_e = step_e2e_groups()
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = float(tt.item())
+        h2d = (model.h.nbytes + model.starts.nbytes + model.ends.nbytes + model.weights.nbytes + R * n + seeds.nbytes + betas.nbytes
+               + sum(np.asarray(g).nbytes for g in groups))
+        d2h = R * n + R * 8
+        e2e = {"value": attempts_per_step_per_gpu * world * e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+               "api": "IsingModel(h, starts, ends, weights) + set_groups + sample(host states) [qa_model_from_ising + "
+                      "qa_model_set_groups + qa_sa_sample_model]"}
+
+    # ---- roofline of the dominant kernel (annealing), from the library's own CUDA events on its stream --------------
+    peak, peak_src = peaks()
+    launches = max(int(stats_acc.get("anneal_launches", 1)), 1)
+    ms_kernel = stats_acc["ms_anneal"] / launches
+    alg = algorithmic_bytes(stats_acc) / launches
+    achieved = alg / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "k_anneal_ref<groups>", "ms_per_launch": ms_kernel,
+                "algorithmic_bytes_per_launch": alg, "survey_formula_GBps": survey_bytes(stats_acc) / launches / (ms_kernel * 1e-3) / 1e9,
+                "acceptance": stats_acc["accepted"] / stats_acc["attempts"],
+                "candidates": stats_acc["candidates"] / stats_acc["attempts"],
+                "bytes_per_attempt": alg * launches / stats_acc["attempts"],
+                "kernel_share_of_step": stats_acc["ms_anneal"] / (elapsed * 1e3)}
+
+    # ---- CPU baseline on rank 0, N = 1 only ---------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        threads = oracle.num_threads()
+        reads = args.cpu_reads or 2 * threads
+        v, dt, _ = run_cpu_sample(model, betas, spb, args.seed, reads, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
+               "sample": f"{reads} reads x {len(betas) * spb} sweeps x {n} vars of the same workload, OpenMP over reads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, model, beta_range),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(stats_acc.get("total_launches", 0)),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "best_energy": float(energies_dev.min().item() + model.offset),
+        }
+        print(json.dumps(line), flush=True)
+    gm.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,9 +126,13 @@ def _canonical(r: np.ndarray, c: np.ndarray, q: np.ndarray):
     return hi[order].astype(np.int32), lo[order].astype(np.int32), np.asarray(q, dtype=np.float64)[order]
 
 
-def _total_weight(w: np.ndarray) -> float:
-    """``G.size(weight='weight')`` = python ``sum`` over edge weights in edge order."""
-    return _seq_sum(np.asarray(w, dtype=np.float64))
+def _total_weight(G, n: int, eu: np.ndarray, ev: np.ndarray, w: np.ndarray) -> float:
+    """``G.size(weight='weight')`` exactly as networkx computes it: sum of the weighted degrees (node order, each degree
+    summed in adjacency order) divided by 2 -- NOT the plain sum of edge weights (differs in the last bits)."""
+    if not isinstance(G, tuple):
+        return float(G.size(weight="weight"))
+    deg = _edge_order_sum(n, eu, ev, np.asarray(w, dtype=np.float64))  # adjacency order of a graph built edge by edge
+    return _seq_sum(deg) / 2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -142,7 +146,7 @@ def cut_balance_model(G, gamma_factor: float, k: float = 8.0, structured: bool =
     """
     labels, eu, ev, w = graph_arrays(G)
     n = len(labels)
-    W = _total_weight(w)
+    W = _total_weight(G, n, eu, ev, w)
     gamma = gamma_factor * W / n
     diag = _edge_order_sum(n, eu, ev, k * w)
     meta = {"kind": "bqm", "builder": "cut_balance", "gamma": gamma, "k": k, "W": W}
@@ -164,7 +168,7 @@ def cut_linear_model(G, gamma_factor: float, k: float) -> LoweredModel:
     """``clustering_bqm_2`` QUBO (BQM_clustering.py:210-236): Q_ii = k*d_i + gamma, Q_uv = -2*k*w, gamma = (W/n)*gamma_factor."""
     labels, eu, ev, w = graph_arrays(G)
     n = len(labels)
-    W = _total_weight(w)
+    W = _total_weight(G, n, eu, ev, w)
     gamma = (W / n) * gamma_factor
     diag = _edge_order_sum(n, eu, ev, k * w) + gamma
     r, c, q = _canonical(eu, ev, k * -2 * w)
@@ -176,7 +180,7 @@ def cut_inequality_bqm(G, gamma_factor: float, size_limit: int, k: float = 8.0) 
     """``clustering_bqm_3`` model (BQM_clustering.py:364-380): k*cut QUBO + size_limit <= sum x <= n/6 as a slack penalty."""
     labels, eu, ev, w = graph_arrays(G)
     n = len(labels)
-    W = _total_weight(w)
+    W = _total_weight(G, n, eu, ev, w)
     gamma = gamma_factor * W / n
     Q = {}
     for c in range(len(w)):
