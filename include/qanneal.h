@@ -48,7 +48,14 @@ extern "C" {
 #define QA_SEED_STREAM 1     /* one xorshift128+ stream across reads == neal(num_reads=R, seed=seeds[0]) */
 /* mode */
 #define QA_MODE_REFERENCE 0  /* neal's sequential variable order, bit-exact against the oracle */
-#define QA_MODE_COLOURED 1   /* graph-coloured parallel update (statistical parity only) */
+#define QA_MODE_THROUGHPUT 1 /* neal's sequential sweep and per-read RNG, local fields re-evaluated from the spins at
+                               every attempt instead of updated incrementally: same algorithm, different fp64 rounding
+                               history -> not bit-exact, statistical parity; needs per-read seeding */
+/* reference-mode kernel selection (both are bit-exact against the oracle) */
+#define QA_KERNEL_AUTO 0
+#define QA_KERNEL_WARP_PER_READ 1  /* one warp per read: any read count, stream seeding */
+#define QA_KERNEL_LOCKSTEP_PUSH 2  /* one warp per 32 reads, read-interleaved fields: many reads (>= ~10^4) */
+#define QA_KERNEL_LOCKSTEP_PULL 3  /* kernel behind QA_MODE_THROUGHPUT (not selectable in reference mode) */
 
 #define QA_MAX_GROUPS 64
 
@@ -82,6 +89,8 @@ int qa_device_count(void);
 int qa_ctx_create(int device_id, qa_ctx **out);
 int qa_ctx_destroy(qa_ctx *ctx);
 int qa_ctx_synchronize(qa_ctx *ctx);
+/* choose the reference-mode annealing kernel (QA_KERNEL_AUTO / _WARP_PER_READ / _LOCKSTEP_PUSH) */
+int qa_ctx_set_kernel(qa_ctx *ctx, int kernel);
 /* number of reads the annealing kernel keeps resident at once (one warp per read) */
 int qa_ctx_resident_reads(qa_ctx *ctx);
 

@@ -19,7 +19,10 @@ QA_OK = 0
 QA_SEED_PER_READ = 0
 QA_SEED_STREAM = 1
 QA_MODE_REFERENCE = 0
-QA_MODE_COLOURED = 1
+QA_MODE_THROUGHPUT = 1
+QA_KERNEL_AUTO = 0
+QA_KERNEL_WARP_PER_READ = 1
+QA_KERNEL_LOCKSTEP_PUSH = 2
 QA_MAX_GROUPS = 64
 
 ERROR_NAMES = {
@@ -77,6 +80,7 @@ SIGNATURES = {
     "qa_ctx_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
     "qa_ctx_destroy": (C.c_int, [_p]),
     "qa_ctx_synchronize": (C.c_int, [_p]),
+    "qa_ctx_set_kernel": (C.c_int, [_p, C.c_int]),
     "qa_ctx_resident_reads": (C.c_int, [_p]),
     "qa_model_from_ising": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p, C.POINTER(_p)]),
     "qa_model_set_groups": (C.c_int, [_p, _i32, _p, _p, _p, _p]),

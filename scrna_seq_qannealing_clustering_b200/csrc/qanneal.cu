@@ -103,11 +103,18 @@ struct AnnealParams {
     int *error_flag;
     int64_t read_begin;          // wave support: global read range [read_begin, read_end)
     int64_t read_end;
+    // lockstep kernels (one warp = 32 reads of one problem)
+    double *fT_scratch;          // [slots][fT_stride]  read-interleaved local fields f[v][lane]
+    int64_t fT_stride;           // n_pad_max * 32
+    int32_t tiles_per_problem;
+    int32_t max_groups;          // stride of the per-thread group counters in shared memory
+    int64_t total_tiles;
 };
 
 enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
 
 constexpr int QA_TPB_MAX = 256;
+// measured on B200 (config 3): lockstep wins from ~3.5 tiles of 32 reads per SM, warp-per-read below that
 constexpr int QA_PREFETCH_CHUNKS = 16;  // run-ahead distance of the L2 prefetch, in 256-byte chunks
 constexpr double QA_TWO64 = 18446744073709551616.0;
 
@@ -380,6 +387,369 @@ __global__ void __launch_bounds__(QA_TPB_MAX, 4) k_anneal_ref(AnnealParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// lockstep kernels: one warp = 32 reads of the same problem; the lanes walk the variables together, every lane
+// owning one read (its own xorshift128+ state, its own spins, its own decisions).  The CSR row of the current
+// variable is shared by the warp, so a neighbour update is ONE coalesced 256-byte reduction for up to 32 reads
+// instead of 32 scattered 8-byte ones, and exp()/RNG run on all lanes at once.
+//   VARIANT 0 "push": local fields f[v][lane] (fp64, read-interleaved) are kept in HBM and updated by
+//                     red.global.add.f64 exactly like the warp-per-read kernel -> bit-exact against the oracle.
+//   VARIANT 1 "pull": no field state at all; f[v] = h_v + sum_j J_vj s_j is re-evaluated from the bit-packed
+//                     spins at every attempt (neal's algorithm, sequential variable order, per-read RNG, but the
+//                     fp64 rounding history of the fields differs) -> throughput mode, statistical parity.
+// Spins live in the read-transposed packed layout packedT[word][read] the energy kernel consumes.
+// ------------------------------------------------------------------------------------------------
+constexpr int QA_LS_TPB = 128;   // threads per block of the lockstep kernels
+constexpr int QA_LS_WPB = QA_LS_TPB / 32;
+constexpr int QA_LS_D = 16;      // variables per staged block
+constexpr int QA_LS_CAP = 384;   // CSR entries staged per block (longer blocks fall back to global loads)
+
+struct LaneStats {
+    unsigned int cand, draws, acc, ties;
+    unsigned long long nbr;
+};
+
+// per-warp staging area in shared memory (double buffered by block parity)
+struct LsStage {
+    double eJ[2][QA_LS_CAP];
+    int ej[2][QA_LS_CAP];
+    int rowp[QA_LS_D + 1];
+    int gm[QA_LS_D];
+    int am[QA_LS_D];
+    int pad_;
+};
+
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// accept test of one variable for every lane (read) of the warp; returns the per-lane accept flag
+__device__ __forceinline__ bool ls_accept(double dE, bool cand, double beta, unsigned long long &s0, unsigned long long &s1,
+                                          LaneStats &st) {
+    bool acc = cand;
+    if (cand && dE > 0.0) {
+        const unsigned long long rnd = rng_next(s0, s1);
+        st.draws++;
+        const double p = exp(-dE * beta) * QA_TWO64;
+        const double rd = __ull2double_rn(rnd);
+        acc = p > rd;
+        if (fabs(p - rd) <= p * 3.5527136788005009e-15) st.ties++;
+    }
+    return acc;
+}
+
+template <int VARIANT, bool GROUPS>
+__device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64_t r, bool active, double *__restrict__ fT,
+                              int *Mcol, unsigned long long &s0, unsigned long long &s1, LaneStats &st, int *error_flag,
+                              double *cur /* smem [QA_LS_D][QA_LS_TPB], this thread's column */, LsStage &sg,
+                              const double *lam_sh, const long long *kap_sh) {
+    const int lane = threadIdx.x & 31;
+    const int n = D.n;
+    const int nch = D.nch;
+    const int64_t rpad = D.rpad;
+    uint32_t *pk = D.packedT + r;  // r < rpad always: padding lanes own a scratch column of packedT
+
+    // ---- pack this read's +-1 bytes (padding lanes and padding variables are +1)
+    for (int wi = 0; wi < nch; ++wi) {
+        uint32_t w = 0xffffffffu;
+        if (active) {
+            const int8_t *row = D.states + r * (int64_t)n + wi * 32;
+            const int lim = min(32, n - wi * 32);
+            for (int i = 0; i < lim; ++i) {
+                const int s = row[i];
+                if (s != 1 && s != -1) atomicExch(error_flag, QA_ERR_STATE);
+                if (s < 0) w &= ~(1u << i);
+            }
+        }
+        pk[(int64_t)wi * rpad] = w;
+    }
+    if (GROUPS) {
+        for (int g = 0; g < D.ngroups; ++g) Mcol[g * QA_LS_TPB] = 0;
+        for (int wi = 0; wi < nch; ++wi) {
+            const uint32_t w = pk[(int64_t)wi * rpad];
+            for (int i = 0; i < 32; ++i) {
+                const int v = wi * 32 + i;
+                const int g = __ldg(D.grp + v);  // uniform
+                if (g >= 0) {
+                    const int a = __ldg(D.coef + v);
+                    Mcol[g * QA_LS_TPB] += ((w >> i) & 1u) ? a : -a;
+                }
+            }
+        }
+    }
+    if (VARIANT == 0) {
+        // local fields in neal's get_flip_energy order, all 32 reads at once (row broadcast, coalesced spin words)
+        for (int v = 0; v < nch * 32; ++v) {
+            double fv = -INFINITY;
+            if (v < n) {
+                fv = __ldg(D.h + v);
+                const int e0 = __ldg(D.rowptr + v), e1 = __ldg(D.rowptr + v + 1);
+                for (int e = e0; e < e1; ++e) {
+                    const int j = __ldg(D.col + e);
+                    const double J = __ldg(D.val + e);
+                    const uint32_t wj = pk[(int64_t)(j >> 5) * rpad];
+                    fv += ((wj >> (j & 31)) & 1u) ? J : -J;
+                }
+            }
+            __stcg(fT + (int64_t)v * 32 + lane, fv);
+        }
+    }
+
+    const int nblk = nch * (32 / QA_LS_D);
+    // software pipeline over blocks of QA_LS_D variables:
+    //   rows of block b+1 are copied to shared memory by cp.async while block b is processed,
+    //   row pointers / group metadata run two blocks ahead in registers,
+    //   (push) the local fields of block b+1 are prefetched into registers and moved to shared memory at the switch.
+    auto load_meta = [&](int blk, int &rp, int &gmv, int &amv) {
+        const int v = blk * QA_LS_D + lane;
+        rp = (lane <= QA_LS_D) ? __ldg(D.rowptr + v) : 0;
+        gmv = -1;
+        amv = 0;
+        if (GROUPS) {
+            if (lane < QA_LS_D) {
+                gmv = __ldg(D.grp + v);
+                amv = __ldg(D.coef + v);
+            }
+        }
+    };
+    auto stage_rows = [&](int buf, int rp) {
+        const int eb = __shfl_sync(FULL_MASK, rp, 0);
+        const int ee = __shfl_sync(FULL_MASK, rp, QA_LS_D);
+        const int cnt = ee - eb;
+        if (cnt <= QA_LS_CAP) {
+            for (int k = lane; k < cnt; k += 32) {
+                cp_async4(&sg.ej[buf][k], D.col + eb + k);
+                cp_async8(&sg.eJ[buf][k], D.val + eb + k);
+            }
+        }
+        cp_async_commit();
+    };
+    int rp_cur, gm_cur, am_cur, rp_nxt, gm_nxt, am_nxt;
+    load_meta(0, rp_cur, gm_cur, am_cur);
+    load_meta(nblk > 1 ? 1 : 0, rp_nxt, gm_nxt, am_nxt);
+    stage_rows(0, rp_cur);
+    double nr[QA_LS_D];
+    if (VARIANT == 0) {
+#pragma unroll
+        for (int i = 0; i < QA_LS_D; ++i) nr[i] = __ldcg(fT + (int64_t)i * 32 + lane);
+    }
+    int parity = 0;
+
+    for (int b = 0; b < P.num_betas; ++b) {
+        const double beta = P.betas[b];
+        const double thr = 44.36142 / beta;
+        for (int sw = 0; sw < P.sweeps_per_beta; ++sw) {
+            uint32_t w = 0;
+            bool dirty = false;
+            for (int blk = 0; blk < nblk; ++blk) {
+                const int v0 = blk * QA_LS_D;
+                const int wi = v0 >> 5;
+                const int sub = v0 & 31;
+                if (sub == 0) {
+                    w = pk[(int64_t)wi * rpad];
+                    dirty = false;
+                }
+                int nb = blk + 1;
+                if (nb == nblk) nb = 0;
+                int nb2 = nb + 1;
+                if (nb2 == nblk) nb2 = 0;
+                // ---- pipeline: rows of the next block, metadata two blocks ahead, fields of the next block
+                __syncwarp();
+                stage_rows(parity ^ 1, rp_nxt);
+                int rp_nn, gm_nn, am_nn;
+                load_meta(nb2, rp_nn, gm_nn, am_nn);
+                if (lane <= QA_LS_D) sg.rowp[lane] = rp_cur;
+                if (GROUPS) {
+                    if (lane < QA_LS_D) {
+                        sg.gm[lane] = gm_cur;
+                        sg.am[lane] = am_cur;
+                    }
+                }
+                bool stale = false;
+                if (VARIANT == 0) {
+#pragma unroll
+                    for (int i = 0; i < QA_LS_D; ++i) cur[i * QA_LS_TPB] = nr[i];
+#pragma unroll
+                    for (int i = 0; i < QA_LS_D; ++i) nr[i] = __ldcg(fT + ((int64_t)nb * QA_LS_D + i) * 32 + lane);
+                }
+                cp_async_wait<1>();
+                __syncwarp();
+                const int eb = sg.rowp[0];
+                const bool staged = (sg.rowp[QA_LS_D] - eb) <= QA_LS_CAP;
+                const int *ej = sg.ej[parity];
+                const double *eJ = sg.eJ[parity];
+
+                for (int i = 0; i < QA_LS_D; ++i) {
+                    const int v = v0 + i;
+                    if (v >= n) break;  // uniform: padding variables
+                    const int e0 = sg.rowp[i], e1 = sg.rowp[i + 1];
+                    const bool up = (w >> (sub + i)) & 1u;
+                    double fv;
+                    if (VARIANT == 0) {
+                        fv = cur[i * QA_LS_TPB];
+                    } else {
+                        // re-evaluate the local field from the spins: h_v + sum_j (+-J) in adjacency order
+                        fv = __ldg(D.h + v);
+                        for (int e = e0; e < e1; e += 8) {
+                            int jq[8];
+                            uint32_t wq[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int ee = min(e + q, e1 - 1);
+                                jq[q] = staged ? ej[ee - eb] : __ldg(D.col + ee);
+                                const int wj = jq[q] >> 5;
+                                wq[q] = (wj != wi) ? pk[(int64_t)wj * rpad] : w;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (e + q < e1) {
+                                    const double J = staged ? eJ[e + q - eb] : __ldg(D.val + e + q);
+                                    fv += ((wq[q] >> (jq[q] & 31)) & 1u) ? J : -J;
+                                }
+                            }
+                        }
+                    }
+                    double dE = up ? -2.0 * fv : 2.0 * fv;
+                    int g = -1, a = 0;
+                    if (GROUPS) {
+                        g = sg.gm[i];
+                        if (g >= 0) {
+                            a = sg.am[i];
+                            const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)Mcol[g * QA_LS_TPB] + kap_sh[g]));
+                            dE = dE + lam_sh[g] * (double)t;
+                        }
+                    }
+                    const bool cand = active && !(dE >= thr);
+                    if (!__any_sync(FULL_MASK, cand)) continue;
+                    if (cand) st.cand++;
+                    const bool acc = ls_accept(dE, cand, beta, s0, s1, st);
+                    if (!__any_sync(FULL_MASK, acc)) continue;
+                    if (acc) {
+                        st.acc++;
+                        st.nbr += (unsigned long long)(e1 - e0);
+                    }
+                    if (VARIANT == 0) {
+                        const double cf = up ? -2.0 : 2.0;  // f[j] += -2*s_v*J  <=> neal dE[j] += 4*s_v*J*s_j
+                        for (int e = e0; e < e1; ++e) {
+                            const int j = staged ? ej[e - eb] : __ldg(D.col + e);
+                            const double d = cf * (staged ? eJ[e - eb] : __ldg(D.val + e));
+                            if (acc) red_add_f64(fT + (int64_t)j * 32 + lane, d);
+                            const int rel = j - v0;  // uniform
+                            if (rel > i && rel < QA_LS_D) {
+                                if (acc) cur[rel * QA_LS_TPB] += d;        // not visited yet in this block
+                            } else if (j >= nb * QA_LS_D && j < nb * QA_LS_D + QA_LS_D) {
+                                stale = true;                               // prefetched registers are stale
+                            }
+                        }
+                    }
+                    if (acc) {
+                        w ^= 1u << (sub + i);
+                        dirty = true;
+                        if (GROUPS) {
+                            if (g >= 0) Mcol[g * QA_LS_TPB] -= 2 * a * (up ? 1 : -1);
+                        }
+                    }
+                }
+                if (VARIANT == 0) {
+                    if (stale) {  // uniform; rare: a flip touched a variable of the prefetched block
+#pragma unroll
+                        for (int i = 0; i < QA_LS_D; ++i) nr[i] = __ldcg(fT + ((int64_t)nb * QA_LS_D + i) * 32 + lane);
+                    }
+                }
+                if ((sub + QA_LS_D == 32 || blk == nblk - 1) && dirty) pk[(int64_t)wi * rpad] = w;
+                rp_cur = rp_nxt; gm_cur = gm_nxt; am_cur = am_nxt;
+                rp_nxt = rp_nn; gm_nxt = gm_nn; am_nxt = am_nn;
+                parity ^= 1;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // ---- final spins back to the caller's +-1 rows
+    if (active) {
+        for (int wi = 0; wi < nch; ++wi) {
+            const uint32_t w = pk[(int64_t)wi * rpad];
+            int8_t *row = D.states + r * (int64_t)n + wi * 32;
+            const int lim = min(32, n - wi * 32);
+            for (int i = 0; i < lim; ++i) row[i] = ((w >> i) & 1u) ? 1 : -1;
+        }
+    }
+}
+
+__host__ __device__ inline size_t ls_smem_bytes(bool push, int max_groups) {
+    size_t b = 0;
+    if (push) b += sizeof(double) * QA_LS_D * QA_LS_TPB;
+    b += sizeof(LsStage) * QA_LS_WPB;
+    b += (sizeof(double) + sizeof(long long)) * (size_t)max_groups;
+    b += sizeof(int) * (size_t)max_groups * QA_LS_TPB;
+    return b;
+}
+
+template <int VARIANT, bool GROUPS>
+__global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P) {
+    extern __shared__ __align__(16) unsigned char ls_smem[];
+    // layout: [cur: D x TPB doubles (push)] [LsStage x warps] [lambda: G doubles] [kappa: G int64] [M: G x TPB ints]
+    unsigned char *sp = ls_smem;
+    double *cur_all = reinterpret_cast<double *>(sp);
+    if (VARIANT == 0) sp += sizeof(double) * QA_LS_D * QA_LS_TPB;
+    LsStage *stages = reinterpret_cast<LsStage *>(sp);
+    sp += sizeof(LsStage) * QA_LS_WPB;
+    double *lam_sh = reinterpret_cast<double *>(sp);
+    sp += sizeof(double) * P.max_groups;
+    long long *kap_sh = reinterpret_cast<long long *>(sp);
+    sp += sizeof(long long) * P.max_groups;
+    int *M_all = reinterpret_cast<int *>(sp);
+    __shared__ unsigned long long next_tile[QA_LS_WPB];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t slot = (int64_t)blockIdx.x * QA_LS_WPB + wib;
+    double *fT = VARIANT == 0 ? P.fT_scratch + slot * P.fT_stride : nullptr;
+    if (GROUPS) {  // groups exist only on single-problem models: one copy of lambda / kappa per block
+        const ProblemDesc &D0 = P.descs[0];
+        for (int g = threadIdx.x; g < D0.ngroups; g += blockDim.x) {
+            lam_sh[g] = D0.lambda[g];
+            kap_sh[g] = D0.kappa[g];
+        }
+    }
+    __syncthreads();
+    LaneStats st = {0, 0, 0, 0, 0};
+    for (;;) {
+        if (lane == 0) next_tile[wib] = atomicAdd(P.counter, 1ull);
+        __syncwarp();
+        const int64_t tile = (int64_t)next_tile[wib];
+        __syncwarp();
+        if (tile >= P.total_tiles) break;
+        const int p = (int)(tile / P.tiles_per_problem);
+        const int64_t tip = tile % P.tiles_per_problem;
+        const ProblemDesc D = P.descs[p];
+        const int64_t r = tip * 32 + lane;
+        const bool active = r < D.reads;
+        const unsigned long long sd = active ? P.seeds[D.read_base + r] : 1ull;
+        unsigned long long s0 = sd ? sd : ~0ull, s1 = 0;
+        lockstep_tile<VARIANT, GROUPS>(D, P, r, active, fT, M_all + threadIdx.x, s0, s1, st, P.error_flag,
+                                       cur_all + threadIdx.x, stages[wib], lam_sh, kap_sh);
+    }
+    // warp-reduce the per-lane counters
+    unsigned long long v[5] = {st.cand, st.draws, st.acc, st.ties, st.nbr};
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL_MASK, v[q], off);
+    if (lane == 0) {
+        atomicAdd(P.stats + ST_CAND, v[0]);
+        atomicAdd(P.stats + ST_DRAWS, v[1]);
+        atomicAdd(P.stats + ST_ACC, v[2]);
+        atomicAdd(P.stats + ST_TIES, v[3]);
+        atomicAdd(P.stats + ST_NBR, v[4]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // energies: neal get_state_energy(), one thread per read, reads on lanes (coalesced packedT loads)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_energy(const ProblemDesc *descs) {
@@ -546,7 +916,8 @@ struct qa_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf f, spw, states, energies, seeds, betas, packed, misc, cubtmp;
+    DevBuf f, spw, fT, states, energies, seeds, betas, packed, misc, cubtmp;
+    int kernel = 0;  // QA_KERNEL_*
     unsigned long long *d_stats = nullptr;  // QA_NSTAT counters + 1 read counter
     int *d_flag = nullptr;
     double *d_best_e = nullptr;
@@ -746,7 +1117,7 @@ int check_schedule(int32_t num_betas, const double *betas, int32_t sweeps_per_be
 // core: anneal all reads of all problems of a model; states/energies already on the device
 int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_states, double *d_energies,
                int32_t num_betas, const double *d_betas, int32_t sweeps_per_beta, const unsigned long long *d_seeds,
-               int32_t seed_mode, qa_interrupt_fn interrupt, void *iuser, qa_stats *st, int64_t *completed) {
+               int32_t seed_mode, int32_t mode, qa_interrupt_fn interrupt, void *iuser, qa_stats *st, int64_t *completed) {
     const int P = M->num_problems;
     const int64_t total_reads = (int64_t)P * reads_per_problem;
     const int32_t rpad = (reads_per_problem + 31) & ~31;
@@ -775,31 +1146,22 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
     }
 
-    // launch geometry: persistent grid, one warp per resident read
     const bool groups = M->ngroups > 0;
-    int wpb = QA_TPB_MAX / 32;
-    if (seed_mode == QA_SEED_STREAM) wpb = 1;
-    else if (total_reads < (int64_t)ctx->num_sms * wpb) wpb = (int)std::max<int64_t>(1, (total_reads + ctx->num_sms - 1) / ctx->num_sms);
-    const int tpb = wpb * 32;
-    int bps = 0;
-    if (groups) QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<true>, tpb, 0));
-    else QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<false>, tpb, 0));
-    if (bps < 1) return fail(QA_ERR_CUDA, "annealing kernel does not fit on an SM");
-    int64_t grid = (int64_t)bps * ctx->num_sms;  // multiple of the SM count
-    const int64_t need = (total_reads + wpb - 1) / wpb;
-    if (need < grid) grid = need;
-    if (seed_mode == QA_SEED_STREAM) grid = 1;
-    const int64_t slots = grid * wpb;
-    const int64_t f_stride = (int64_t)M->nch_max * 32;
-    const int64_t spw_stride = ((int64_t)M->nch_max + 31) & ~31ll;
-    rc = ensure(ctx->f, (size_t)slots * f_stride * sizeof(double));
-    if (!rc) rc = ensure(ctx->spw, (size_t)slots * spw_stride * sizeof(uint32_t));
-    if (rc) return rc;
+    // kernel choice: warp-per-read (any read count, stream seeding) or lockstep (32 reads per warp)
+    int kernel = QA_KERNEL_WARP_PER_READ;
+    if (mode == QA_MODE_THROUGHPUT) kernel = QA_KERNEL_LOCKSTEP_PULL;
+    else if (ctx->kernel == QA_KERNEL_LOCKSTEP_PUSH && seed_mode == QA_SEED_PER_READ) kernel = QA_KERNEL_LOCKSTEP_PUSH;
+    else if (ctx->kernel == QA_KERNEL_AUTO && seed_mode == QA_SEED_PER_READ && (int64_t)reads_per_problem >= 32 &&
+             2 * total_reads >= (int64_t)ctx->num_sms * 32 * 7)
+        kernel = QA_KERNEL_LOCKSTEP_PUSH;
+    if (kernel == QA_KERNEL_LOCKSTEP_PULL && seed_mode != QA_SEED_PER_READ)
+        return fail(QA_ERR_ARG, "throughput mode needs per-read seeding");
 
     QA_CUDA(cudaMemsetAsync(ctx->d_stats, 0, (QA_NSTAT + 1) * sizeof(unsigned long long), ctx->stream));
     QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
 
     AnnealParams A;
+    memset(&A, 0, sizeof(A));
     A.descs = M->d_descs;
     A.num_problems = P;
     A.reads_per_problem = reads_per_problem;
@@ -809,33 +1171,100 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
     A.sweeps_per_beta = sweeps_per_beta;
     A.seeds = d_seeds;
     A.seed_mode = seed_mode;
-    A.f_scratch = (double *)ctx->f.p;
-    A.spw_scratch = (uint32_t *)ctx->spw.p;
-    A.f_stride = f_stride;
-    A.spw_stride = spw_stride;
     A.counter = ctx->d_stats + QA_NSTAT;
     A.stats = ctx->d_stats;
     A.error_flag = ctx->d_flag;
 
-    // without an interrupt callback the whole job is one launch; with one, read waves of `slots` reads
-    const int64_t wave = (interrupt && seed_mode != QA_SEED_STREAM) ? slots : total_reads;
-    QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     int64_t done = 0;
     bool interrupted = false;
-    while (done < total_reads) {
-        A.read_begin = done;
-        A.read_end = std::min(total_reads, done + wave);
+    if (kernel == QA_KERNEL_WARP_PER_READ) {
+        // launch geometry: persistent grid, one warp per resident read
+        int wpb = QA_TPB_MAX / 32;
+        if (seed_mode == QA_SEED_STREAM) wpb = 1;
+        else if (total_reads < (int64_t)ctx->num_sms * wpb) wpb = (int)std::max<int64_t>(1, (total_reads + ctx->num_sms - 1) / ctx->num_sms);
+        const int tpb = wpb * 32;
+        int bps = 0;
+        if (groups) QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<true>, tpb, 0));
+        else QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_anneal_ref<false>, tpb, 0));
+        if (bps < 1) return fail(QA_ERR_CUDA, "annealing kernel does not fit on an SM");
+        int64_t grid = (int64_t)bps * ctx->num_sms;  // multiple of the SM count
+        const int64_t need = (total_reads + wpb - 1) / wpb;
+        if (need < grid) grid = need;
+        if (seed_mode == QA_SEED_STREAM) grid = 1;
+        const int64_t slots = grid * wpb;
+        const int64_t f_stride = (int64_t)M->nch_max * 32;
+        const int64_t spw_stride = ((int64_t)M->nch_max + 31) & ~31ll;
+        rc = ensure(ctx->f, (size_t)slots * f_stride * sizeof(double));
+        if (!rc) rc = ensure(ctx->spw, (size_t)slots * spw_stride * sizeof(uint32_t));
+        if (rc) return rc;
+        A.f_scratch = (double *)ctx->f.p;
+        A.spw_scratch = (uint32_t *)ctx->spw.p;
+        A.f_stride = f_stride;
+        A.spw_stride = spw_stride;
+
+        // without an interrupt callback the whole job is one launch; with one, read waves of `slots` reads
+        const int64_t wave = (interrupt && seed_mode != QA_SEED_STREAM) ? slots : total_reads;
+        QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+        while (done < total_reads) {
+            A.read_begin = done;
+            A.read_end = std::min(total_reads, done + wave);
+            QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
+            if (groups) k_anneal_ref<true><<<(unsigned)grid, tpb, 0, ctx->stream>>>(A);
+            else k_anneal_ref<false><<<(unsigned)grid, tpb, 0, ctx->stream>>>(A);
+            QA_CUDA(cudaGetLastError());
+            ctx->launches++;
+            if (st) st->anneal_launches++;
+            done = A.read_end;
+            if (interrupt && done < total_reads) {
+                QA_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (interrupt(iuser)) { interrupted = true; break; }
+            }
+        }
+    } else {
+        // lockstep: one warp = 32 reads of one problem
+        const bool push = kernel == QA_KERNEL_LOCKSTEP_PUSH;
+        const int tpp = (reads_per_problem + 31) / 32;
+        const int64_t total_tiles = (int64_t)P * tpp;
+        const size_t smem = ls_smem_bytes(push, std::max(M->ngroups, 1));
+        const void *fn = nullptr;
+        if (push) fn = groups ? (const void *)k_anneal_lockstep<0, true> : (const void *)k_anneal_lockstep<0, false>;
+        else fn = groups ? (const void *)k_anneal_lockstep<1, true> : (const void *)k_anneal_lockstep<1, false>;
+        QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int bps = 0;
+        QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, QA_LS_TPB, smem, cudaOccupancyDefault));
+        if (bps < 1) return fail(QA_ERR_CUDA, "lockstep kernel does not fit on an SM");
+        const int wpb = QA_LS_TPB / 32;
+        int64_t grid = (int64_t)bps * ctx->num_sms;
+        const int64_t need = (total_tiles + wpb - 1) / wpb;
+        // spread few tiles over all SMs: prefer more blocks with idle warps to fewer full blocks
+        if (need < grid) grid = std::min<int64_t>(grid, std::max<int64_t>(need, std::min<int64_t>(total_tiles, (int64_t)ctx->num_sms)));
+        const int64_t fT_stride = (int64_t)M->nch_max * 32 * 32;
+        if (push) {
+            size_t free_b = 0, total_b = 0;
+            QA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t per_slot = (size_t)fT_stride * sizeof(double);
+            const size_t budget = (size_t)((double)(free_b + ctx->fT.bytes) * 0.85);
+            int64_t max_slots = (int64_t)(budget / per_slot);
+            if (max_slots < wpb) return fail(QA_ERR_CUDA, "not enough device memory for one block of local fields");
+            if (grid * wpb > max_slots) grid = max_slots / wpb;
+            rc = ensure(ctx->fT, (size_t)grid * wpb * per_slot);
+            if (rc) return rc;
+            A.fT_scratch = (double *)ctx->fT.p;
+        }
+        A.fT_stride = fT_stride;
+        A.tiles_per_problem = tpp;
+        A.total_tiles = total_tiles;
+        A.max_groups = std::max(M->ngroups, 1);
+        A.read_begin = 0;
+        A.read_end = total_reads;
+        QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
         QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
-        if (groups) k_anneal_ref<true><<<(unsigned)grid, tpb, 0, ctx->stream>>>(A);
-        else k_anneal_ref<false><<<(unsigned)grid, tpb, 0, ctx->stream>>>(A);
+        void *args[] = {&A};
+        QA_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(QA_LS_TPB), args, smem, ctx->stream));
         QA_CUDA(cudaGetLastError());
         ctx->launches++;
         if (st) st->anneal_launches++;
-        done = A.read_end;
-        if (interrupt && done < total_reads) {
-            QA_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (interrupt(iuser)) { interrupted = true; break; }
-        }
+        done = total_reads;
     }
     QA_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     {
@@ -877,7 +1306,7 @@ int sample_common(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *s
     if (!ctx || !M) return fail(QA_ERR_ARG, "null context or model");
     if (M->ctx != ctx) return fail(QA_ERR_ARG, "model belongs to another context");
     if (reads_per_problem < 0) return fail(QA_ERR_ARG, "negative num_reads");
-    if (mode != QA_MODE_REFERENCE) return fail(QA_ERR_ARG, "unknown mode");
+    if (mode != QA_MODE_REFERENCE && mode != QA_MODE_THROUGHPUT) return fail(QA_ERR_ARG, "unknown mode");
     if (seed_mode != QA_SEED_PER_READ && seed_mode != QA_SEED_STREAM) return fail(QA_ERR_ARG, "unknown seed_mode");
     if (seed_mode == QA_SEED_STREAM && M->num_problems != 1) return fail(QA_ERR_ARG, "stream seeding needs a single problem");
     int rc = check_schedule(num_betas, beta_schedule, sweeps_per_beta);
@@ -929,7 +1358,7 @@ int sample_common(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *s
 
     int64_t completed = 0;
     rc = run_anneal(ctx, M, reads_per_problem, d_states, d_energies, num_betas, d_betas, sweeps_per_beta, d_seeds, seed_mode,
-                    interrupt, iuser, &st, &completed);
+                    mode, interrupt, iuser, &st, &completed);
     if (rc) return rc;
 
     QA_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -994,7 +1423,7 @@ int qa_ctx_destroy(qa_ctx *ctx) {
     if (!ctx) return QA_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    release(ctx->f); release(ctx->spw); release(ctx->states); release(ctx->energies); release(ctx->seeds);
+    release(ctx->f); release(ctx->spw); release(ctx->fT); release(ctx->states); release(ctx->energies); release(ctx->seeds);
     release(ctx->betas); release(ctx->packed); release(ctx->misc); release(ctx->cubtmp);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -1009,6 +1438,14 @@ int qa_ctx_destroy(qa_ctx *ctx) {
 int qa_ctx_synchronize(qa_ctx *ctx) {
     if (!ctx) return fail(QA_ERR_ARG, "null context");
     QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_ctx_set_kernel(qa_ctx *ctx, int kernel) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (kernel != QA_KERNEL_AUTO && kernel != QA_KERNEL_WARP_PER_READ && kernel != QA_KERNEL_LOCKSTEP_PUSH)
+        return fail(QA_ERR_ARG, "kernel must be QA_KERNEL_AUTO, QA_KERNEL_WARP_PER_READ or QA_KERNEL_LOCKSTEP_PUSH");
+    ctx->kernel = kernel;
     return QA_OK;
 }
 

@@ -54,6 +54,10 @@ class Context:
     def __exit__(self, *exc):
         self.close()
 
+    def set_kernel(self, kernel: int):
+        """Reference-mode kernel: _lib.QA_KERNEL_AUTO / QA_KERNEL_WARP_PER_READ / QA_KERNEL_LOCKSTEP_PUSH."""
+        check(_lib.load().qa_ctx_set_kernel(self._h, int(kernel)))
+
     @property
     def resident_reads(self) -> int:
         return check(_lib.load().qa_ctx_resident_reads(self._h))

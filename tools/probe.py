@@ -18,6 +18,8 @@ ap.add_argument("--sweeps", type=int, default=100)
 ap.add_argument("--model", default="cqm")
 ap.add_argument("--hot", type=float, default=None)
 ap.add_argument("--cold", type=float, default=None)
+ap.add_argument("--kernel", type=int, default=1)
+ap.add_argument("--mode", type=int, default=0)
 a = ap.parse_args()
 t = time.time()
 graph, _ = snn.synthetic_snn(a.cells, k=5, seed=0)
@@ -39,12 +41,13 @@ seeds = schedule.per_read_seeds(1, a.reads)
 rng = np.random.default_rng(0)
 states = (rng.integers(0, 2, size=(a.reads, m.num_variables), dtype=np.int8) * 2 - 1).astype(np.int8)
 with Context(0) as ctx:
+    ctx.set_kernel(a.kernel)
     gm = IsingModel(ctx, m.h, m.starts, m.ends, m.weights)
     if groups is not None:
         gm.set_groups(*groups)
     for it in range(2):
         s = states.copy()
-        e, st, done = gm.sample(s, betas, spb, seeds)
+        e, st, done = gm.sample(s, betas, spb, seeds, mode=a.mode)
         att = st.attempts
         print(f"iter {it}: anneal {st.ms_anneal:.1f} ms  energy {st.ms_energy:.1f} ms  h2d {st.ms_h2d:.1f} d2h {st.ms_d2h:.1f}  "
               f"attempts/s {att / st.ms_anneal * 1e3:.3e}  acc {st.accepted / att:.4f} cand {st.candidates / att:.4f} "
