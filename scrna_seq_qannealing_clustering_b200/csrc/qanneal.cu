@@ -82,6 +82,11 @@ struct ProblemDesc {
     int8_t *states;         // [reads][n]
     uint32_t *packedT;      // [nch][rpad] final spins, bit i of word (c, r) = spin of variable 32c+i (1: +1)
     double *energies;       // [reads]
+    // block word tables of the pull variant (null until built): for every block of 16 variables the distinct spin words
+    // its CSR rows refer to, and per CSR entry the index of its word in that list (255 = the block's own word)
+    const int32_t *bw_ptr;      // [nblk + 1], this problem's first block at index 0 (values are global offsets)
+    const int32_t *bw_words;    // global array
+    const unsigned short *ent_slot; // indexed like col: slot | (bit << 8)
 };
 
 struct AnnealParams {
@@ -135,6 +140,12 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 __device__ __forceinline__ void red_add_f64(double *addr, double v) {
     // fire-and-forget fp64 reduction performed at L2 (RED.E.ADD.F64); round-to-nearest like the CPU add
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ void red_add_f64_if(double *addr, double v, bool pred) {
+    // predicated form: no branch / reconvergence point in the neighbour loop
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(addr), "d"(v), "r"((int)pred)
+                 : "memory");
 }
 
 struct WarpStats {
@@ -402,6 +413,8 @@ constexpr int QA_LS_TPB = 128;   // threads per block of the lockstep kernels
 constexpr int QA_LS_WPB = QA_LS_TPB / 32;
 constexpr int QA_LS_D = 16;      // variables per staged block
 constexpr int QA_LS_CAP = 384;   // CSR entries staged per block (longer blocks fall back to global loads)
+constexpr int QA_LS_CAPW = 48;   // distinct spin words per block held in shared memory by the pull variant
+constexpr int QA_SWITCH_PERMILLE = 30;  // throughput mode: pull while > 3 % of the attempts of a sweep are accepted
 
 struct LaneStats {
     unsigned int cand, draws, acc, ties;
@@ -410,12 +423,17 @@ struct LaneStats {
 
 // per-warp staging area in shared memory (double buffered by block parity)
 struct LsStage {
-    double eJ[2][QA_LS_CAP];
-    int ej[2][QA_LS_CAP];
+    double eJ[2][QA_LS_CAP];                    // couplings of the block's CSR entries
+    int ej[2][QA_LS_CAP];                       // neighbour indices
     int rowp[QA_LS_D + 1];
     int gm[QA_LS_D];
     int am[QA_LS_D];
     int pad_;
+};
+struct LsStagePull {                            // only the throughput-mode kernel carries these
+    double hb[2][QA_LS_D];                      // h of the block's variables
+    unsigned int slotw[2][QA_LS_CAP / 2 + 2];   // per-entry (slot | bit << 8) as 16-bit pairs; slot 255 = own word
+    int bw[2][QA_LS_CAPW];                      // distinct spin words referenced by the block
 };
 
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
@@ -443,71 +461,91 @@ __device__ __forceinline__ bool ls_accept(double dE, bool cand, double beta, uns
     return acc;
 }
 
+struct LsCtx {
+    const ProblemDesc &D;
+    const AnnealParams &P;
+    int64_t r;
+    bool active;
+    double *fT;
+    int *Mcol;
+    double *cur;            // smem [QA_LS_D][QA_LS_TPB], this thread's column
+    LsStage &sg;
+    LsStagePull &sp;        // valid in the throughput-mode kernel only
+    uint32_t *words;        // smem [QA_LS_CAPW][32], this lane's column (pull)
+    const double *lam_sh;
+    const long long *kap_sh;
+};
+
+// h_v + sum over the CSR row of (+-J) in adjacency order, spin words loaded 8 at a time (loads batched, adds sequential)
+__device__ __forceinline__ double ls_field_direct(const ProblemDesc &D, const uint32_t *pk, int64_t rpad, int v, int e0, int e1,
+                                                  int own_word, uint32_t w_own) {
+    double fv = __ldg(D.h + v);
+    for (int e = e0; e < e1; e += 8) {
+        int jq[8];
+        uint32_t wq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            jq[q] = __ldg(D.col + min(e + q, e1 - 1));
+            const int wj = jq[q] >> 5;
+            wq[q] = (wj != own_word) ? pk[(int64_t)wj * rpad] : w_own;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (e + q < e1) {
+                const double J = __ldg(D.val + e + q);
+                fv += ((wq[q] >> (jq[q] & 31)) & 1u) ? J : -J;
+            }
+        }
+    }
+    return fv;
+}
+
+// local fields in neal's get_flip_energy order, all 32 reads at once (row broadcast, coalesced spin words)
+__device__ void ls_init_fields(const LsCtx &c) {
+    const ProblemDesc &D = c.D;
+    const int lane = threadIdx.x & 31;
+    const uint32_t *pk = D.packedT + c.r;
+    int e0 = __ldg(D.rowptr);
+    for (int v = 0; v < D.nch * 32; ++v) {
+        double fv = -INFINITY;
+        const int e1 = __ldg(D.rowptr + v + 1);
+        if (v < D.n) fv = ls_field_direct(D, pk, D.rpad, v, e0, e1, -1, 0u);
+        e0 = e1;
+        __stcg(c.fT + (int64_t)v * 32 + lane, fv);
+    }
+}
+
+// Runs sweeps from (bi, swi) on; returns true when the schedule is finished, false when the pull variant hands over to
+// the push variant (bi, swi then name the next sweep).  VARIANT 0 = push (bit-exact), 1 = pull (recomputed fields).
 template <int VARIANT, bool GROUPS>
-__device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64_t r, bool active, double *__restrict__ fT,
-                              int *Mcol, unsigned long long &s0, unsigned long long &s1, LaneStats &st, int *error_flag,
-                              double *cur /* smem [QA_LS_D][QA_LS_TPB], this thread's column */, LsStage &sg,
-                              const double *lam_sh, const long long *kap_sh) {
+__device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, unsigned long long &s0,
+                          unsigned long long &s1, LaneStats &st) {
+    const ProblemDesc &D = c.D;
+    const AnnealParams &P = c.P;
+    LsStage &sg = c.sg;
+    LsStagePull &sp = c.sp;
     const int lane = threadIdx.x & 31;
     const int n = D.n;
     const int nch = D.nch;
     const int64_t rpad = D.rpad;
-    uint32_t *pk = D.packedT + r;  // r < rpad always: padding lanes own a scratch column of packedT
-
-    // ---- pack this read's +-1 bytes (padding lanes and padding variables are +1)
-    for (int wi = 0; wi < nch; ++wi) {
-        uint32_t w = 0xffffffffu;
-        if (active) {
-            const int8_t *row = D.states + r * (int64_t)n + wi * 32;
-            const int lim = min(32, n - wi * 32);
-            for (int i = 0; i < lim; ++i) {
-                const int s = row[i];
-                if (s != 1 && s != -1) atomicExch(error_flag, QA_ERR_STATE);
-                if (s < 0) w &= ~(1u << i);
-            }
-        }
-        pk[(int64_t)wi * rpad] = w;
-    }
-    if (GROUPS) {
-        for (int g = 0; g < D.ngroups; ++g) Mcol[g * QA_LS_TPB] = 0;
-        for (int wi = 0; wi < nch; ++wi) {
-            const uint32_t w = pk[(int64_t)wi * rpad];
-            for (int i = 0; i < 32; ++i) {
-                const int v = wi * 32 + i;
-                const int g = __ldg(D.grp + v);  // uniform
-                if (g >= 0) {
-                    const int a = __ldg(D.coef + v);
-                    Mcol[g * QA_LS_TPB] += ((w >> i) & 1u) ? a : -a;
-                }
-            }
-        }
-    }
-    if (VARIANT == 0) {
-        // local fields in neal's get_flip_energy order, all 32 reads at once (row broadcast, coalesced spin words)
-        for (int v = 0; v < nch * 32; ++v) {
-            double fv = -INFINITY;
-            if (v < n) {
-                fv = __ldg(D.h + v);
-                const int e0 = __ldg(D.rowptr + v), e1 = __ldg(D.rowptr + v + 1);
-                for (int e = e0; e < e1; ++e) {
-                    const int j = __ldg(D.col + e);
-                    const double J = __ldg(D.val + e);
-                    const uint32_t wj = pk[(int64_t)(j >> 5) * rpad];
-                    fv += ((wj >> (j & 31)) & 1u) ? J : -J;
-                }
-            }
-            __stcg(fT + (int64_t)v * 32 + lane, fv);
-        }
-    }
-
+    uint32_t *pk = D.packedT + c.r;
+    double *fT = c.fT;
+    double *cur = c.cur;
+    int *Mcol = c.Mcol;
+    const bool active = c.active;
+    const bool tables = VARIANT == 1 && D.bw_ptr != nullptr;
     const int nblk = nch * (32 / QA_LS_D);
+    const unsigned nactive = __popc(__ballot_sync(FULL_MASK, active));
+
     // software pipeline over blocks of QA_LS_D variables:
-    //   rows of block b+1 are copied to shared memory by cp.async while block b is processed,
-    //   row pointers / group metadata run two blocks ahead in registers,
-    //   (push) the local fields of block b+1 are prefetched into registers and moved to shared memory at the switch.
+    //   rows (and, for pull, h / slot bytes / distinct-word list) of block b+1 are copied to shared memory by cp.async while
+    //   block b is processed; row pointers and group metadata run two blocks ahead in registers; (push) the local fields
+    //   of block b+1 are prefetched into registers and moved to shared memory at the switch.
     auto load_meta = [&](int blk, int &rp, int &gmv, int &amv) {
         const int v = blk * QA_LS_D + lane;
-        rp = (lane <= QA_LS_D) ? __ldg(D.rowptr + v) : 0;
+        rp = 0;
+        if (lane <= QA_LS_D) rp = __ldg(D.rowptr + v);
+        else if (tables && lane <= QA_LS_D + 2) rp = __ldg(D.bw_ptr + blk + (lane - QA_LS_D - 1));
         gmv = -1;
         amv = 0;
         if (GROUPS) {
@@ -517,7 +555,7 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
             }
         }
     };
-    auto stage_rows = [&](int buf, int rp) {
+    auto stage_rows = [&](int buf, int blk, int rp) {
         const int eb = __shfl_sync(FULL_MASK, rp, 0);
         const int ee = __shfl_sync(FULL_MASK, rp, QA_LS_D);
         const int cnt = ee - eb;
@@ -526,26 +564,43 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
                 cp_async4(&sg.ej[buf][k], D.col + eb + k);
                 cp_async8(&sg.eJ[buf][k], D.val + eb + k);
             }
+            if (VARIANT == 1) {
+                if (tables) {
+                    const int b0 = __shfl_sync(FULL_MASK, rp, QA_LS_D + 1);
+                    const int b1 = __shfl_sync(FULL_MASK, rp, QA_LS_D + 2);
+                    for (int k = lane; k < b1 - b0; k += 32) cp_async4(&sp.bw[buf][k], D.bw_words + b0 + k);
+                    const int a0 = eb & ~1;                       // 16-bit entries staged as aligned 32-bit words
+                    const int nw2 = ((ee + 1) & ~1) - a0;
+                    for (int k = lane * 2; k < nw2; k += 64) cp_async4(&sp.slotw[buf][k >> 1], D.ent_slot + a0 + k);
+                }
+            }
+        }
+        if (VARIANT == 1) {
+            const int v = blk * QA_LS_D + lane;
+            if (lane < QA_LS_D && v < n) cp_async8(&sp.hb[buf][lane], D.h + v);
         }
         cp_async_commit();
     };
     int rp_cur, gm_cur, am_cur, rp_nxt, gm_nxt, am_nxt;
     load_meta(0, rp_cur, gm_cur, am_cur);
     load_meta(nblk > 1 ? 1 : 0, rp_nxt, gm_nxt, am_nxt);
-    stage_rows(0, rp_cur);
+    __syncwarp();
+    stage_rows(0, 0, rp_cur);
     double nr[QA_LS_D];
     if (VARIANT == 0) {
 #pragma unroll
         for (int i = 0; i < QA_LS_D; ++i) nr[i] = __ldcg(fT + (int64_t)i * 32 + lane);
     }
     int parity = 0;
+    bool finished = true;
 
-    for (int b = 0; b < P.num_betas; ++b) {
-        const double beta = P.betas[b];
+    for (; bi < P.num_betas; ++bi, swi = 0) {
+        const double beta = P.betas[bi];
         const double thr = 44.36142 / beta;
-        for (int sw = 0; sw < P.sweeps_per_beta; ++sw) {
+        for (; swi < P.sweeps_per_beta; ++swi) {
             uint32_t w = 0;
             bool dirty = false;
+            unsigned sweep_acc = 0;
             for (int blk = 0; blk < nblk; ++blk) {
                 const int v0 = blk * QA_LS_D;
                 const int wi = v0 >> 5;
@@ -560,7 +615,7 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
                 if (nb2 == nblk) nb2 = 0;
                 // ---- pipeline: rows of the next block, metadata two blocks ahead, fields of the next block
                 __syncwarp();
-                stage_rows(parity ^ 1, rp_nxt);
+                stage_rows(parity ^ 1, nb, rp_nxt);
                 int rp_nn, gm_nn, am_nn;
                 load_meta(nb2, rp_nn, gm_nn, am_nn);
                 if (lane <= QA_LS_D) sg.rowp[lane] = rp_cur;
@@ -583,6 +638,26 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
                 const bool staged = (sg.rowp[QA_LS_D] - eb) <= QA_LS_CAP;
                 const int *ej = sg.ej[parity];
                 const double *eJ = sg.eJ[parity];
+                bool tabled = false;
+                const unsigned short *slots = nullptr;
+                if (VARIANT == 1) {
+                    if (tables && staged) {
+                        const int nbw = __shfl_sync(FULL_MASK, rp_cur, QA_LS_D + 2) - __shfl_sync(FULL_MASK, rp_cur, QA_LS_D + 1);
+                        tabled = !(nbw == 1 && sp.bw[parity][0] < 0);
+                        if (tabled) {
+                            // this lane's copy of every distinct spin word the block refers to (its own word stays in `w`)
+                            for (int s = 0; s < nbw; s += 8) {
+                                uint32_t t[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) t[q] = (s + q < nbw) ? pk[(int64_t)sp.bw[parity][s + q] * rpad] : 0u;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    if (s + q < nbw) c.words[(s + q) * 32] = t[q];
+                            }
+                            slots = reinterpret_cast<const unsigned short *>(sp.slotw[parity]) + (eb & 1);
+                        }
+                    }
+                }
 
                 for (int i = 0; i < QA_LS_D; ++i) {
                     const int v = v0 + i;
@@ -594,24 +669,19 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
                         fv = cur[i * QA_LS_TPB];
                     } else {
                         // re-evaluate the local field from the spins: h_v + sum_j (+-J) in adjacency order
-                        fv = __ldg(D.h + v);
-                        for (int e = e0; e < e1; e += 8) {
-                            int jq[8];
-                            uint32_t wq[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int ee = min(e + q, e1 - 1);
-                                jq[q] = staged ? ej[ee - eb] : __ldg(D.col + ee);
-                                const int wj = jq[q] >> 5;
-                                wq[q] = (wj != wi) ? pk[(int64_t)wj * rpad] : w;
+                        if (tabled) {
+                            fv = sp.hb[parity][i];
+#pragma unroll 4
+                            for (int e = e0; e < e1; ++e) {
+                                const int k = e - eb;
+                                const unsigned sb = slots[k];             // low byte: slot (255 = own word), high byte: bit
+                                const unsigned sl = sb & 255u;
+                                const uint32_t wv = (sl == 255u) ? w : c.words[sl * 32];
+                                const double J = eJ[k];
+                                fv += ((wv >> (sb >> 8)) & 1u) ? J : -J;
                             }
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (e + q < e1) {
-                                    const double J = staged ? eJ[e + q - eb] : __ldg(D.val + e + q);
-                                    fv += ((wq[q] >> (jq[q] & 31)) & 1u) ? J : -J;
-                                }
-                            }
+                        } else {
+                            fv = ls_field_direct(D, pk, rpad, v, e0, e1, wi, w);
                         }
                     }
                     double dE = up ? -2.0 * fv : 2.0 * fv;
@@ -620,32 +690,52 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
                         g = sg.gm[i];
                         if (g >= 0) {
                             a = sg.am[i];
-                            const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)Mcol[g * QA_LS_TPB] + kap_sh[g]));
-                            dE = dE + lam_sh[g] * (double)t;
+                            const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)Mcol[g * QA_LS_TPB] + c.kap_sh[g]));
+                            dE = dE + c.lam_sh[g] * (double)t;
                         }
                     }
                     const bool cand = active && !(dE >= thr);
                     if (!__any_sync(FULL_MASK, cand)) continue;
                     if (cand) st.cand++;
                     const bool acc = ls_accept(dE, cand, beta, s0, s1, st);
-                    if (!__any_sync(FULL_MASK, acc)) continue;
+                    const unsigned accm = __ballot_sync(FULL_MASK, acc);
+                    if (accm == 0) continue;
+                    sweep_acc += __popc(accm);
                     if (acc) {
                         st.acc++;
                         st.nbr += (unsigned long long)(e1 - e0);
                     }
                     if (VARIANT == 0) {
                         const double cf = up ? -2.0 : 2.0;  // f[j] += -2*s_v*J  <=> neal dE[j] += 4*s_v*J*s_j
-                        for (int e = e0; e < e1; ++e) {
-                            const int j = staged ? ej[e - eb] : __ldg(D.col + e);
-                            const double d = cf * (staged ? eJ[e - eb] : __ldg(D.val + e));
-                            if (acc) red_add_f64(fT + (int64_t)j * 32 + lane, d);
-                            const int rel = j - v0;  // uniform
-                            if (rel > i && rel < QA_LS_D) {
-                                if (acc) cur[rel * QA_LS_TPB] += d;        // not visited yet in this block
-                            } else if (j >= nb * QA_LS_D && j < nb * QA_LS_D + QA_LS_D) {
-                                stale = true;                               // prefetched registers are stale
+                        double *fTl = fT + lane;
+                        const int nbv0 = nb * QA_LS_D;
+                        const unsigned later = (unsigned)(QA_LS_D - 1 - i);  // variables of this block not visited yet
+                        unsigned hit_next = 0;
+                        if (staged) {
+#pragma unroll 4
+                            for (int k = e0 - eb; k < e1 - eb; ++k) {
+                                const int j = ej[k];
+                                const double d = cf * eJ[k];
+                                red_add_f64_if(fTl + (int64_t)j * 32, d, acc);
+                                const unsigned rel = (unsigned)(j - v - 1);       // uniform
+                                if (rel < later) {
+                                    if (acc) cur[(rel + i + 1) * QA_LS_TPB] += d;  // patch the staged copy
+                                }
+                                hit_next |= (unsigned)((unsigned)(j - nbv0) < (unsigned)QA_LS_D);
+                            }
+                        } else {
+                            for (int e = e0; e < e1; ++e) {
+                                const int j = __ldg(D.col + e);
+                                const double d = cf * __ldg(D.val + e);
+                                red_add_f64_if(fTl + (int64_t)j * 32, d, acc);
+                                const unsigned rel = (unsigned)(j - v - 1);
+                                if (rel < later) {
+                                    if (acc) cur[(rel + i + 1) * QA_LS_TPB] += d;
+                                }
+                                hit_next |= (unsigned)((unsigned)(j - nbv0) < (unsigned)QA_LS_D);
                             }
                         }
+                        stale = stale || (hit_next != 0);  // prefetched registers of the next block are stale
                     }
                     if (acc) {
                         w ^= 1u << (sub + i);
@@ -666,13 +756,74 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
                 rp_nxt = rp_nn; gm_nxt = gm_nn; am_nxt = am_nn;
                 parity ^= 1;
             }
+            if (VARIANT == 1) {
+                // hand over to the push variant once flips are rare (uniform decision: warp-wide count of this sweep)
+                if (allow_switch && (unsigned long long)sweep_acc * 1000ull < (unsigned long long)QA_SWITCH_PERMILLE * n * nactive) {
+                    ++swi;
+                    finished = false;
+                    goto done;
+                }
+            }
         }
     }
+done:
     cp_async_wait<0>();
     __syncwarp();
+    if (!finished && swi >= P.sweeps_per_beta) {
+        swi = 0;
+        ++bi;
+    }
+    return finished && true;
+}
+
+// VARIANT 0: push only (reference mode).  VARIANT 1: throughput mode = pull while flips are frequent, then push.
+template <int VARIANT, bool GROUPS>
+__device__ void lockstep_tile(const LsCtx &c, unsigned long long &s0, unsigned long long &s1, LaneStats &st, int *error_flag) {
+    const ProblemDesc &D = c.D;
+    const int n = D.n;
+    const int nch = D.nch;
+    const int64_t rpad = D.rpad;
+    const int64_t r = c.r;
+    uint32_t *pk = D.packedT + r;  // r < rpad always: padding lanes own a scratch column of packedT
+
+    // ---- pack this read's +-1 bytes (padding lanes and padding variables are +1)
+    for (int wi = 0; wi < nch; ++wi) {
+        uint32_t w = 0xffffffffu;
+        if (c.active) {
+            const int8_t *row = D.states + r * (int64_t)n + wi * 32;
+            const int lim = min(32, n - wi * 32);
+            for (int i = 0; i < lim; ++i) {
+                const int s = row[i];
+                if (s != 1 && s != -1) atomicExch(error_flag, QA_ERR_STATE);
+                if (s < 0) w &= ~(1u << i);
+            }
+        }
+        pk[(int64_t)wi * rpad] = w;
+    }
+    if (GROUPS) {
+        for (int g = 0; g < D.ngroups; ++g) c.Mcol[g * QA_LS_TPB] = 0;
+        for (int wi = 0; wi < nch; ++wi) {
+            const uint32_t w = pk[(int64_t)wi * rpad];
+            for (int i = 0; i < 32; ++i) {
+                const int v = wi * 32 + i;
+                const int g = __ldg(D.grp + v);  // uniform
+                if (g >= 0) {
+                    const int a = __ldg(D.coef + v);
+                    c.Mcol[g * QA_LS_TPB] += ((w >> i) & 1u) ? a : -a;
+                }
+            }
+        }
+    }
+    int bi = 0, swi = 0;
+    bool finished = false;
+    if (VARIANT == 1) finished = ls_sweeps<1, GROUPS>(c, bi, swi, c.fT != nullptr, s0, s1, st);
+    if (!finished) {
+        ls_init_fields(c);
+        ls_sweeps<0, GROUPS>(c, bi, swi, false, s0, s1, st);
+    }
 
     // ---- final spins back to the caller's +-1 rows
-    if (active) {
+    if (c.active) {
         for (int wi = 0; wi < nch; ++wi) {
             const uint32_t w = pk[(int64_t)wi * rpad];
             int8_t *row = D.states + r * (int64_t)n + wi * 32;
@@ -682,24 +833,28 @@ __device__ void lockstep_tile(const ProblemDesc &D, const AnnealParams &P, int64
     }
 }
 
-__host__ __device__ inline size_t ls_smem_bytes(bool push, int max_groups) {
-    size_t b = 0;
-    if (push) b += sizeof(double) * QA_LS_D * QA_LS_TPB;
+__host__ __device__ inline size_t ls_smem_bytes(bool pull, int max_groups) {
+    size_t b = sizeof(double) * QA_LS_D * QA_LS_TPB;   // cur (push phase)
     b += sizeof(LsStage) * QA_LS_WPB;
+    if (pull) b += sizeof(LsStagePull) * QA_LS_WPB + sizeof(uint32_t) * QA_LS_CAPW * QA_LS_TPB;
     b += (sizeof(double) + sizeof(long long)) * (size_t)max_groups;
     b += sizeof(int) * (size_t)max_groups * QA_LS_TPB;
     return b;
 }
 
 template <int VARIANT, bool GROUPS>
-__global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P) {
+__global__ void __launch_bounds__(QA_LS_TPB, VARIANT == 0 ? 3 : 2) k_anneal_lockstep(AnnealParams P) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
-    // layout: [cur: D x TPB doubles (push)] [LsStage x warps] [lambda: G doubles] [kappa: G int64] [M: G x TPB ints]
+    // layout: [cur: D x TPB doubles] [LsStage x warps] [words: CAPW x TPB (pull)] [lambda: G] [kappa: G] [M: G x TPB ints]
     unsigned char *sp = ls_smem;
     double *cur_all = reinterpret_cast<double *>(sp);
-    if (VARIANT == 0) sp += sizeof(double) * QA_LS_D * QA_LS_TPB;
+    sp += sizeof(double) * QA_LS_D * QA_LS_TPB;
     LsStage *stages = reinterpret_cast<LsStage *>(sp);
     sp += sizeof(LsStage) * QA_LS_WPB;
+    LsStagePull *pstages = reinterpret_cast<LsStagePull *>(sp);
+    if (VARIANT == 1) sp += sizeof(LsStagePull) * QA_LS_WPB;
+    uint32_t *words_all = reinterpret_cast<uint32_t *>(sp);
+    if (VARIANT == 1) sp += sizeof(uint32_t) * QA_LS_CAPW * QA_LS_TPB;
     double *lam_sh = reinterpret_cast<double *>(sp);
     sp += sizeof(double) * P.max_groups;
     long long *kap_sh = reinterpret_cast<long long *>(sp);
@@ -709,7 +864,7 @@ __global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t slot = (int64_t)blockIdx.x * QA_LS_WPB + wib;
-    double *fT = VARIANT == 0 ? P.fT_scratch + slot * P.fT_stride : nullptr;
+    double *fT = P.fT_scratch ? P.fT_scratch + slot * P.fT_stride : nullptr;
     if (GROUPS) {  // groups exist only on single-problem models: one copy of lambda / kappa per block
         const ProblemDesc &D0 = P.descs[0];
         for (int g = threadIdx.x; g < D0.ngroups; g += blockDim.x) {
@@ -732,8 +887,9 @@ __global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P
         const bool active = r < D.reads;
         const unsigned long long sd = active ? P.seeds[D.read_base + r] : 1ull;
         unsigned long long s0 = sd ? sd : ~0ull, s1 = 0;
-        lockstep_tile<VARIANT, GROUPS>(D, P, r, active, fT, M_all + threadIdx.x, s0, s1, st, P.error_flag,
-                                       cur_all + threadIdx.x, stages[wib], lam_sh, kap_sh);
+        const LsCtx c = {D, P, r, active, fT, M_all + threadIdx.x, cur_all + threadIdx.x, stages[wib],
+                         pstages[VARIANT == 1 ? wib : 0], words_all + wib * (QA_LS_CAPW * 32) + lane, lam_sh, kap_sh};
+        lockstep_tile<VARIANT, GROUPS>(c, s0, s1, st, P.error_flag);
     }
     // warp-reduce the per-lane counters
     unsigned long long v[5] = {st.cand, st.draws, st.acc, st.ties, st.nbr};
@@ -945,6 +1101,10 @@ struct qa_model {
     long long *kappa = nullptr;
     ProblemDesc *d_descs = nullptr;
     std::vector<ProblemDesc> descs;  // host mirror (pointers are device pointers)
+    // block word tables of the pull variant (built on first use)
+    int32_t *bw_ptr = nullptr, *bw_words = nullptr;
+    unsigned short *ent_slot = nullptr;
+    bool tables_built = false;
 };
 
 namespace {
@@ -1072,6 +1232,7 @@ int finalize_descs(qa_model *M) {
         D.ends = M->ends + c0;
         D.w = M->w + c0;
         D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
+        D.bw_ptr = nullptr; D.bw_words = nullptr; D.ent_slot = nullptr;
         M->n_max = std::max(M->n_max, D.n);
     }
     M->nch_max = (M->n_max + 31) / 32;
@@ -1099,6 +1260,77 @@ int model_create(qa_ctx *ctx, int32_t P, const int64_t *var_off, const int64_t *
         return rc;
     }
     *out = M;
+    return QA_OK;
+}
+
+// Block word tables for the pull variant: per block of QA_LS_D variables the distinct spin words (32 variables each) its
+// CSR rows refer to, and per CSR entry the slot of its word in that list.  Built once per model on the host from the
+// device-built CSR (a setup step, O(entries)); blocks that exceed the shared-memory capacities get a -1 sentinel.
+int build_word_tables(qa_model *M) {
+    if (M->tables_built) return QA_OK;
+    qa_ctx *ctx = M->ctx;
+    const int64_t entries = 2 * M->m_total;
+    const int64_t rows_alloc = M->n_total + 64 + 1;
+    std::vector<int32_t> rowptr(rows_alloc), col(std::max<int64_t>(entries, 1));
+    QA_CUDA(cudaMemcpy(rowptr.data(), M->rowptr, rows_alloc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (entries) QA_CUDA(cudaMemcpy(col.data(), M->col, entries * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> bw_ptr, bw_words;
+    std::vector<unsigned short> slot(std::max<int64_t>(entries, 1) + 8, 255);
+    std::vector<int64_t> blk_base(M->num_problems + 1, 0);
+    bw_ptr.push_back(0);
+    std::vector<int32_t> stamp, slot_of;
+    for (int p = 0; p < M->num_problems; ++p) {
+        const int64_t v_off = M->var_off[p];
+        const int n = (int)(M->var_off[p + 1] - v_off);
+        const int nch = (n + 31) / 32;
+        const int nblk = nch * (32 / QA_LS_D);
+        blk_base[p] = (int64_t)bw_ptr.size() - 1;
+        stamp.assign(nch, -1);
+        slot_of.assign(nch, 0);
+        for (int b = 0; b < nblk; ++b) {
+            const int v0 = b * QA_LS_D;
+            const int64_t eb = rowptr[v_off + std::min(v0, n)];
+            const int64_t ee = rowptr[v_off + std::min(v0 + QA_LS_D, n)];
+            const size_t first = bw_words.size();
+            const int own = v0 >> 5;
+            bool ok = (ee - eb) <= QA_LS_CAP;
+            for (int64_t e = eb; e < ee && ok; ++e) {
+                const int wj = col[e] >> 5;
+                const unsigned short bit = (unsigned short)((col[e] & 31) << 8);
+                if (wj == own) { slot[e] = 255 | bit; continue; }
+                if (stamp[wj] != b) {
+                    if (bw_words.size() - first >= (size_t)QA_LS_CAPW) { ok = false; break; }
+                    stamp[wj] = b;
+                    slot_of[wj] = (int32_t)(bw_words.size() - first);
+                    bw_words.push_back(wj);
+                }
+                slot[e] = (unsigned short)slot_of[wj] | bit;
+            }
+            if (!ok) {
+                bw_words.resize(first);
+                bw_words.push_back(-1);  // sentinel: block not tabled, kernel falls back to direct loads
+                for (int w = 0; w < nch; ++w) if (stamp[w] == b) stamp[w] = -1;
+            }
+            bw_ptr.push_back((int32_t)bw_words.size());
+        }
+        // one extra pointer per problem so that the two-ahead metadata loads of the last block stay in range
+    }
+    blk_base[M->num_problems] = (int64_t)bw_ptr.size() - 1;
+    for (int k = 0; k < 4; ++k) bw_ptr.push_back((int32_t)bw_words.size());
+    if (bw_words.empty()) bw_words.push_back(-1);
+    QA_CUDA(cudaMalloc((void **)&M->bw_ptr, bw_ptr.size() * sizeof(int32_t)));
+    QA_CUDA(cudaMalloc((void **)&M->bw_words, bw_words.size() * sizeof(int32_t)));
+    QA_CUDA(cudaMalloc((void **)&M->ent_slot, slot.size() * sizeof(unsigned short)));
+    QA_CUDA(cudaMemcpyAsync(M->bw_ptr, bw_ptr.data(), bw_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(M->bw_words, bw_words.data(), bw_words.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(M->ent_slot, slot.data(), slot.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < M->num_problems; ++p) {
+        M->descs[p].bw_ptr = M->bw_ptr + blk_base[p];
+        M->descs[p].bw_words = M->bw_words;
+        M->descs[p].ent_slot = M->ent_slot;
+    }
+    M->tables_built = true;
     return QA_OK;
 }
 
@@ -1222,12 +1454,12 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         }
     } else {
         // lockstep: one warp = 32 reads of one problem
-        const bool push = kernel == QA_KERNEL_LOCKSTEP_PUSH;
+        const bool pull = kernel == QA_KERNEL_LOCKSTEP_PULL;
         const int tpp = (reads_per_problem + 31) / 32;
         const int64_t total_tiles = (int64_t)P * tpp;
-        const size_t smem = ls_smem_bytes(push, std::max(M->ngroups, 1));
+        const size_t smem = ls_smem_bytes(pull, std::max(M->ngroups, 1));
         const void *fn = nullptr;
-        if (push) fn = groups ? (const void *)k_anneal_lockstep<0, true> : (const void *)k_anneal_lockstep<0, false>;
+        if (!pull) fn = groups ? (const void *)k_anneal_lockstep<0, true> : (const void *)k_anneal_lockstep<0, false>;
         else fn = groups ? (const void *)k_anneal_lockstep<1, true> : (const void *)k_anneal_lockstep<1, false>;
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
@@ -1239,17 +1471,27 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         // spread few tiles over all SMs: prefer more blocks with idle warps to fewer full blocks
         if (need < grid) grid = std::min<int64_t>(grid, std::max<int64_t>(need, std::min<int64_t>(total_tiles, (int64_t)ctx->num_sms)));
         const int64_t fT_stride = (int64_t)M->nch_max * 32 * 32;
-        if (push) {
+        {
+            // read-interleaved local fields for the resident tiles (push kernel; push phase of the throughput mode)
             size_t free_b = 0, total_b = 0;
             QA_CUDA(cudaMemGetInfo(&free_b, &total_b));
             const size_t per_slot = (size_t)fT_stride * sizeof(double);
             const size_t budget = (size_t)((double)(free_b + ctx->fT.bytes) * 0.85);
             int64_t max_slots = (int64_t)(budget / per_slot);
-            if (max_slots < wpb) return fail(QA_ERR_CUDA, "not enough device memory for one block of local fields");
-            if (grid * wpb > max_slots) grid = max_slots / wpb;
-            rc = ensure(ctx->fT, (size_t)grid * wpb * per_slot);
+            if (max_slots < wpb) {
+                if (!pull) return fail(QA_ERR_CUDA, "not enough device memory for one block of local fields");
+                A.fT_scratch = nullptr;  // throughput mode then recomputes fields for the whole schedule
+            } else {
+                if (grid * wpb > max_slots) grid = max_slots / wpb;
+                rc = ensure(ctx->fT, (size_t)grid * wpb * per_slot);
+                if (rc) return rc;
+                A.fT_scratch = (double *)ctx->fT.p;
+            }
+        }
+        if (pull) {
+            rc = build_word_tables(M);
             if (rc) return rc;
-            A.fT_scratch = (double *)ctx->fT.p;
+            QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
         }
         A.fT_stride = fT_stride;
         A.tiles_per_problem = tpp;
@@ -1538,7 +1780,8 @@ int qa_model_destroy(qa_model *M) {
     if (!M) return QA_OK;
     cudaSetDevice(M->ctx->device);
     cudaStreamSynchronize(M->ctx->stream);
-    void *ptrs[] = {M->h, M->starts, M->ends, M->w, M->rowptr, M->col, M->val, M->grp, M->coef, M->lambda, M->kappa, M->d_descs};
+    void *ptrs[] = {M->h, M->starts, M->ends, M->w, M->rowptr, M->col, M->val, M->grp, M->coef, M->lambda, M->kappa, M->d_descs,
+                    M->bw_ptr, M->bw_words, M->ent_slot};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete M;
     return QA_OK;

@@ -129,8 +129,8 @@ class B200SimulatedAnnealingSampler:
     def _run(self, model: LoweredModel, vartype, t0, beta_range, num_reads, num_sweeps, num_sweeps_per_beta,
              beta_schedule_type, seed, interrupt_function, beta_schedule, initial_states, initial_states_generator, mode,
              seed_mode, sort_result, aggregate) -> SampleSet:
-        if mode not in ("reference",):
-            raise ValueError("mode must be 'reference'")
+        if mode not in ("reference", "throughput"):
+            raise ValueError("mode must be 'reference' (bit-exact neal order) or 'throughput' (fields recomputed from spins)")
         if seed_mode not in ("per_read", "stream"):
             raise ValueError("seed_mode must be 'per_read' or 'stream'")
         if interrupt_function is not None and not callable(interrupt_function):
@@ -174,7 +174,8 @@ class B200SimulatedAnnealingSampler:
             t1 = time.perf_counter_ns()
             energies, st, done = gm.sample(local_states, betas, spb, seeds,
                                            seed_mode=_lib.QA_SEED_STREAM if seed_mode == "stream" else _lib.QA_SEED_PER_READ,
-                                           mode=_lib.QA_MODE_REFERENCE, interrupt_function=interrupt_function)
+                                           mode=_lib.QA_MODE_THROUGHPUT if mode == "throughput" else _lib.QA_MODE_REFERENCE,
+                                           interrupt_function=interrupt_function)
             t2 = time.perf_counter_ns()
         finally:
             gm.close()
