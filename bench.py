@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=16384)
     ap.add_argument("--clusters", type=int, default=8)
-    ap.add_argument("--reads", type=int, default=18944, help="reads per GPU per step (148 SMs x 4 warps x 32 reads)")
+    ap.add_argument("--reads", type=int, default=37888, help="reads per GPU per step (148 SMs x 8 warps x 32 reads)")
     ap.add_argument("--sweeps", type=int, default=50,
                     help="points of the geometric beta schedule per step (the full config-3 job is 1000; the per-attempt "
                          "phase mix, hence attempts/s, is the same for any length over the same beta range)")

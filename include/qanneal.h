@@ -146,6 +146,27 @@ int qa_energy_argmin(qa_ctx *ctx, qa_model *model, int32_t num_reads, const int8
                      double *energies_out, double *best_energy, int64_t *best_index,
                      qa_stats *stats_out);
 
+/* ---- model builders on the device --------------------------------------------------------------------------------
+ * Graph = n nodes and m_edges weighted edges (eu[e], ev[e], w[e]) in the order networkx yields G.edges (host or device
+ * pointers).  Each builder restates one Q-dict construction of the reference on the GPU and leaves a resident model in
+ * dimod's to_numpy_vectors order; every floating-point accumulation keeps the reference's order, so h / couplers are
+ * bit-identical to the Python builders (models.py).  offset_out: E_binary(x) = E_spin(s) + offset.
+ *   qa_build_cut_balance   BQM_clustering.py:29-47   k*cut + gamma*S(S-n), gamma = gamma_factor*W/n; balance term as 1 group
+ *   qa_build_subsampling   QA_subsampling.py:26-35   sum (1-w)(x_u x_v - x_u - x_v) + gamma*sum x   (P = 1 in the reference)
+ *   qa_build_dqm_onehot    DQM_clustering.py:29-43   one-hot expansion (variable i*K + c), penalty*(sum_c x_ic - 1)^2,
+ *                                                    cluster-size term as K groups; intended = 0: set_* semantics as written
+ *   qa_build_cqm_penalty   CQM_clustering.py:30-48   objective + A*(one-hot)^2 + B*(N_j - min_size - slack_j)^2 as K groups
+ */
+int qa_build_cut_balance(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
+                         double gamma_factor, double k, qa_model **out, double *offset_out, double *gamma_out);
+int qa_build_subsampling(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
+                         double gamma, double P, qa_model **out, double *offset_out);
+int qa_build_dqm_onehot(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
+                        int32_t num_cases, double gamma, double penalty, int32_t intended, qa_model **out, double *offset_out);
+int qa_build_cqm_penalty(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
+                         int32_t num_clusters, int32_t min_size, double onehot_penalty, double size_penalty, qa_model **out,
+                         double *offset_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,47 @@ class Context:
     def synchronize(self):
         check(_lib.load().qa_ctx_synchronize(self._h))
 
+    # -- model construction on the device (qa_build_*): graph = (n, eu, ev, w) in G.edges order ---
+    def _graph_args(self, graph):
+        n, eu, ev, w = graph
+        if not _is_tensor(eu):
+            eu = np.ascontiguousarray(eu, dtype=np.int32)
+            ev = np.ascontiguousarray(ev, dtype=np.int32)
+            w = np.ascontiguousarray(w, dtype=np.float64)
+        return int(n), int(eu.shape[0]), eu, ev, w
+
+    def build_cut_balance(self, graph, gamma_factor: float, k: float = 8.0):
+        """``clustering_bqm`` model (BQM_clustering.py:29-47), balance term as a rank-1 group.  -> (IsingModel, offset, gamma)"""
+        n, m, eu, ev, w = self._graph_args(graph)
+        hm, off, gam = C.c_void_p(), C.c_double(), C.c_double()
+        check(_lib.load().qa_build_cut_balance(self._h, n, m, ptr(eu), ptr(ev), ptr(w), float(gamma_factor), float(k), C.byref(hm),
+                                               C.byref(off), C.byref(gam)))
+        return IsingModel._from_handle(self, hm), float(off.value), float(gam.value)
+
+    def build_subsampling(self, graph, gamma: float, P: float = 1.0):
+        """``graph_subsampling`` model (QA_subsampling.py:26-35).  -> (IsingModel, offset)"""
+        n, m, eu, ev, w = self._graph_args(graph)
+        hm, off = C.c_void_p(), C.c_double()
+        check(_lib.load().qa_build_subsampling(self._h, n, m, ptr(eu), ptr(ev), ptr(w), float(gamma), float(P), C.byref(hm),
+                                               C.byref(off)))
+        return IsingModel._from_handle(self, hm), float(off.value)
+
+    def build_dqm_onehot(self, graph, num_cases: int, gamma: float, penalty: float, semantics: str = "as_written"):
+        """``clustering_dqm`` model (DQM_clustering.py:29-43), one-hot expanded and structured.  -> (IsingModel, offset)"""
+        n, m, eu, ev, w = self._graph_args(graph)
+        hm, off = C.c_void_p(), C.c_double()
+        check(_lib.load().qa_build_dqm_onehot(self._h, n, m, ptr(eu), ptr(ev), ptr(w), int(num_cases), float(gamma), float(penalty),
+                                              1 if semantics == "intended" else 0, C.byref(hm), C.byref(off)))
+        return IsingModel._from_handle(self, hm), float(off.value)
+
+    def build_cqm_penalty(self, graph, num_clusters: int, min_size: int, onehot_penalty: float, size_penalty: float):
+        """``clustering_cqm`` model (CQM_clustering.py:30-48) lowered to penalties.  -> (IsingModel, offset)"""
+        n, m, eu, ev, w = self._graph_args(graph)
+        hm, off = C.c_void_p(), C.c_double()
+        check(_lib.load().qa_build_cqm_penalty(self._h, n, m, ptr(eu), ptr(ev), ptr(w), int(num_clusters), int(min_size),
+                                               float(onehot_penalty), float(size_penalty), C.byref(hm), C.byref(off)))
+        return IsingModel._from_handle(self, hm), float(off.value)
+
     # -- neal's general_simulated_annealing, one shot, host or device buffers --------------------
     def sample_ising(self, h, starts, ends, weights, states, beta_schedule, sweeps_per_beta, seeds,
                      seed_mode=_lib.QA_SEED_PER_READ, mode=_lib.QA_MODE_REFERENCE, energies=None):
