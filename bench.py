@@ -160,10 +160,9 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
     model, beta_range, betas, spb = build_workload(args)
-    threads = oracle.num_threads()
-    reads = args.cpu_reads or threads
+    threads = len(os.sched_getaffinity(0))  # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    reads = args.cpu_reads or 8 * threads
     for _ in range(max(0, min(args.warmup, 1))):
         run_cpu_sample(model, betas[: max(1, len(betas) // 50)], spb, args.seed, threads, threads)
     rates, times = [], []
@@ -318,9 +317,8 @@ def main():
     # ---- CPU baseline on rank 0, N = 1 only ---------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        threads = oracle.num_threads()
-        reads = args.cpu_reads or 2 * threads
+        threads = len(os.sched_getaffinity(0))
+        reads = args.cpu_reads or 8 * threads
         v, dt, _ = run_cpu_sample(model, betas, spb, args.seed, reads, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
                "sample": f"{reads} reads x {len(betas) * spb} sweeps x {n} vars of the same workload, OpenMP over reads"}

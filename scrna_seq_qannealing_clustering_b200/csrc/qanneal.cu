@@ -413,7 +413,8 @@ constexpr int QA_LS_TPB = 128;   // threads per block of the lockstep kernels
 constexpr int QA_LS_WPB = QA_LS_TPB / 32;
 constexpr int QA_LS_D = 16;      // variables per staged block
 constexpr int QA_LS_CAP = 384;   // CSR entries staged per block (longer blocks fall back to global loads)
-constexpr int QA_LS_CAPW = 48;   // distinct spin words per block held in shared memory by the pull variant
+constexpr int QA_LS_CAPW = 32;   // distinct spin words per block held in shared memory (aliases the `cur` staging area)
+static_assert(QA_LS_CAPW * sizeof(uint32_t) <= QA_LS_D * sizeof(double), "spin-word staging must fit into the field staging area");
 constexpr int QA_SWITCH_PERMILLE = 30;  // throughput mode: pull while > 3 % of the attempts of a sweep are accepted
 
 struct LaneStats {
@@ -430,7 +431,7 @@ struct LsStage {
     int am[QA_LS_D];
     int pad_;
 };
-struct LsStagePull {                            // only the throughput-mode kernel carries these
+struct LsStagePull {                            // field (re-)evaluation from spins: init pass and pull variant
     double hb[2][QA_LS_D];                      // h of the block's variables
     unsigned int slotw[2][QA_LS_CAP / 2 + 2];   // per-entry (slot | bit << 8) as 16-bit pairs; slot 255 = own word
     int bw[2][QA_LS_CAPW];                      // distinct spin words referenced by the block
@@ -468,10 +469,10 @@ struct LsCtx {
     bool active;
     double *fT;
     int *Mcol;
-    double *cur;            // smem [QA_LS_D][QA_LS_TPB], this thread's column
+    double *cur;            // smem, per warp [QA_LS_D][32], this lane's column
     LsStage &sg;
-    LsStagePull &sp;        // valid in the throughput-mode kernel only
-    uint32_t *words;        // smem [QA_LS_CAPW][32], this lane's column (pull)
+    LsStagePull &sp;
+    uint32_t *words;        // smem [QA_LS_CAPW][32], this lane's column; aliases `cur` (never live at the same time)
     const double *lam_sh;
     const long long *kap_sh;
 };
@@ -500,23 +501,10 @@ __device__ __forceinline__ double ls_field_direct(const ProblemDesc &D, const ui
     return fv;
 }
 
-// local fields in neal's get_flip_energy order, all 32 reads at once (row broadcast, coalesced spin words)
-__device__ void ls_init_fields(const LsCtx &c) {
-    const ProblemDesc &D = c.D;
-    const int lane = threadIdx.x & 31;
-    const uint32_t *pk = D.packedT + c.r;
-    int e0 = __ldg(D.rowptr);
-    for (int v = 0; v < D.nch * 32; ++v) {
-        double fv = -INFINITY;
-        const int e1 = __ldg(D.rowptr + v + 1);
-        if (v < D.n) fv = ls_field_direct(D, pk, D.rpad, v, e0, e1, -1, 0u);
-        e0 = e1;
-        __stcg(c.fT + (int64_t)v * 32 + lane, fv);
-    }
-}
-
 // Runs sweeps from (bi, swi) on; returns true when the schedule is finished, false when the pull variant hands over to
-// the push variant (bi, swi then name the next sweep).  VARIANT 0 = push (bit-exact), 1 = pull (recomputed fields).
+// the push variant (bi, swi then name the next sweep).  VARIANT 0 = push (bit-exact), 1 = pull (recomputed fields),
+// 2 = one pass that only evaluates the local fields from the spins and stores them (neal get_flip_energy order): the
+// initialisation of the push variant, run through the same staged pipeline as the pull variant.
 template <int VARIANT, bool GROUPS>
 __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, unsigned long long &s0,
                           unsigned long long &s1, LaneStats &st) {
@@ -533,7 +521,7 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
     double *cur = c.cur;
     int *Mcol = c.Mcol;
     const bool active = c.active;
-    const bool tables = VARIANT == 1 && D.bw_ptr != nullptr;
+    const bool tables = VARIANT >= 1 && D.bw_ptr != nullptr;
     const int nblk = nch * (32 / QA_LS_D);
     const unsigned nactive = __popc(__ballot_sync(FULL_MASK, active));
 
@@ -564,7 +552,7 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                 cp_async4(&sg.ej[buf][k], D.col + eb + k);
                 cp_async8(&sg.eJ[buf][k], D.val + eb + k);
             }
-            if (VARIANT == 1) {
+            if (VARIANT >= 1) {
                 if (tables) {
                     const int b0 = __shfl_sync(FULL_MASK, rp, QA_LS_D + 1);
                     const int b1 = __shfl_sync(FULL_MASK, rp, QA_LS_D + 2);
@@ -575,7 +563,7 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                 }
             }
         }
-        if (VARIANT == 1) {
+        if (VARIANT >= 1) {
             const int v = blk * QA_LS_D + lane;
             if (lane < QA_LS_D && v < n) cp_async8(&sp.hb[buf][lane], D.h + v);
         }
@@ -594,10 +582,12 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
     int parity = 0;
     bool finished = true;
 
-    for (; bi < P.num_betas; ++bi, swi = 0) {
-        const double beta = P.betas[bi];
+    const int nbeta = VARIANT == 2 ? 1 : P.num_betas;
+    const int nspb = VARIANT == 2 ? 1 : P.sweeps_per_beta;
+    for (; bi < nbeta; ++bi, swi = 0) {
+        const double beta = VARIANT == 2 ? 1.0 : P.betas[bi];
         const double thr = 44.36142 / beta;
-        for (; swi < P.sweeps_per_beta; ++swi) {
+        for (; swi < nspb; ++swi) {
             uint32_t w = 0;
             bool dirty = false;
             unsigned sweep_acc = 0;
@@ -626,9 +616,10 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                     }
                 }
                 bool stale = false;
+                bool blk_dirty = false;
                 if (VARIANT == 0) {
 #pragma unroll
-                    for (int i = 0; i < QA_LS_D; ++i) cur[i * QA_LS_TPB] = nr[i];
+                    for (int i = 0; i < QA_LS_D; ++i) cur[i * 32] = nr[i];
 #pragma unroll
                     for (int i = 0; i < QA_LS_D; ++i) nr[i] = __ldcg(fT + ((int64_t)nb * QA_LS_D + i) * 32 + lane);
                 }
@@ -640,7 +631,7 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                 const double *eJ = sg.eJ[parity];
                 bool tabled = false;
                 const unsigned short *slots = nullptr;
-                if (VARIANT == 1) {
+                if (VARIANT >= 1) {
                     if (tables && staged) {
                         const int nbw = __shfl_sync(FULL_MASK, rp_cur, QA_LS_D + 2) - __shfl_sync(FULL_MASK, rp_cur, QA_LS_D + 1);
                         tabled = !(nbw == 1 && sp.bw[parity][0] < 0);
@@ -666,7 +657,7 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                     const bool up = (w >> (sub + i)) & 1u;
                     double fv;
                     if (VARIANT == 0) {
-                        fv = cur[i * QA_LS_TPB];
+                        fv = cur[i * 32];
                     } else {
                         // re-evaluate the local field from the spins: h_v + sum_j (+-J) in adjacency order
                         if (tabled) {
@@ -682,6 +673,10 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                             }
                         } else {
                             fv = ls_field_direct(D, pk, rpad, v, e0, e1, wi, w);
+                        }
+                        if (VARIANT == 2) {
+                            __stcg(fT + (int64_t)v * 32 + lane, fv);
+                            continue;
                         }
                     }
                     double dE = up ? -2.0 * fv : 2.0 * fv;
@@ -709,30 +704,35 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                         const double cf = up ? -2.0 : 2.0;  // f[j] += -2*s_v*J  <=> neal dE[j] += 4*s_v*J*s_j
                         double *fTl = fT + lane;
                         const int nbv0 = nb * QA_LS_D;
-                        const unsigned later = (unsigned)(QA_LS_D - 1 - i);  // variables of this block not visited yet
                         unsigned hit_next = 0;
+                        // neighbours inside the staged block are updated in shared memory only (the block is written back
+                        // once, below); all others get one predicated fire-and-forget reduction
                         if (staged) {
 #pragma unroll 4
                             for (int k = e0 - eb; k < e1 - eb; ++k) {
                                 const int j = ej[k];
                                 const double d = cf * eJ[k];
-                                red_add_f64_if(fTl + (int64_t)j * 32, d, acc);
-                                const unsigned rel = (unsigned)(j - v - 1);       // uniform
-                                if (rel < later) {
-                                    if (acc) cur[(rel + i + 1) * QA_LS_TPB] += d;  // patch the staged copy
+                                const unsigned rel = (unsigned)(j - v0);          // uniform
+                                if (rel < (unsigned)QA_LS_D) {
+                                    if (acc) cur[rel * 32] += d;
+                                    blk_dirty = true;
+                                } else {
+                                    red_add_f64_if(fTl + (int64_t)j * 32, d, acc);
+                                    hit_next |= (unsigned)((unsigned)(j - nbv0) < (unsigned)QA_LS_D);
                                 }
-                                hit_next |= (unsigned)((unsigned)(j - nbv0) < (unsigned)QA_LS_D);
                             }
                         } else {
                             for (int e = e0; e < e1; ++e) {
                                 const int j = __ldg(D.col + e);
                                 const double d = cf * __ldg(D.val + e);
-                                red_add_f64_if(fTl + (int64_t)j * 32, d, acc);
-                                const unsigned rel = (unsigned)(j - v - 1);
-                                if (rel < later) {
-                                    if (acc) cur[(rel + i + 1) * QA_LS_TPB] += d;
+                                const unsigned rel = (unsigned)(j - v0);
+                                if (rel < (unsigned)QA_LS_D) {
+                                    if (acc) cur[rel * 32] += d;
+                                    blk_dirty = true;
+                                } else {
+                                    red_add_f64_if(fTl + (int64_t)j * 32, d, acc);
+                                    hit_next |= (unsigned)((unsigned)(j - nbv0) < (unsigned)QA_LS_D);
                                 }
-                                hit_next |= (unsigned)((unsigned)(j - nbv0) < (unsigned)QA_LS_D);
                             }
                         }
                         stale = stale || (hit_next != 0);  // prefetched registers of the next block are stale
@@ -746,6 +746,10 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                     }
                 }
                 if (VARIANT == 0) {
+                    if (blk_dirty) {  // uniform: write the staged fields of this block back (coalesced 256 B rows)
+#pragma unroll
+                        for (int i = 0; i < QA_LS_D; ++i) __stcg(fT + ((int64_t)v0 + i) * 32 + lane, cur[i * 32]);
+                    }
                     if (stale) {  // uniform; rare: a flip touched a variable of the prefetched block
 #pragma unroll
                         for (int i = 0; i < QA_LS_D; ++i) nr[i] = __ldcg(fT + ((int64_t)nb * QA_LS_D + i) * 32 + lane);
@@ -818,7 +822,8 @@ __device__ void lockstep_tile(const LsCtx &c, unsigned long long &s0, unsigned l
     bool finished = false;
     if (VARIANT == 1) finished = ls_sweeps<1, GROUPS>(c, bi, swi, c.fT != nullptr, s0, s1, st);
     if (!finished) {
-        ls_init_fields(c);
+        int ib = 0, is = 0;
+        ls_sweeps<2, false>(c, ib, is, false, s0, s1, st);  // local fields from the current spins
         ls_sweeps<0, GROUPS>(c, bi, swi, false, s0, s1, st);
     }
 
@@ -833,28 +838,26 @@ __device__ void lockstep_tile(const LsCtx &c, unsigned long long &s0, unsigned l
     }
 }
 
-__host__ __device__ inline size_t ls_smem_bytes(bool pull, int max_groups) {
-    size_t b = sizeof(double) * QA_LS_D * QA_LS_TPB;   // cur (push phase)
-    b += sizeof(LsStage) * QA_LS_WPB;
-    if (pull) b += sizeof(LsStagePull) * QA_LS_WPB + sizeof(uint32_t) * QA_LS_CAPW * QA_LS_TPB;
+__host__ __device__ inline size_t ls_smem_bytes(int max_groups) {
+    size_t b = sizeof(double) * QA_LS_D * QA_LS_TPB;   // cur (push phases) / spin words (field evaluation phases)
+    b += (sizeof(LsStage) + sizeof(LsStagePull)) * QA_LS_WPB;
     b += (sizeof(double) + sizeof(long long)) * (size_t)max_groups;
     b += sizeof(int) * (size_t)max_groups * QA_LS_TPB;
     return b;
 }
 
 template <int VARIANT, bool GROUPS>
-__global__ void __launch_bounds__(QA_LS_TPB, VARIANT == 0 ? 3 : 2) k_anneal_lockstep(AnnealParams P) {
+__global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
-    // layout: [cur: D x TPB doubles] [LsStage x warps] [words: CAPW x TPB (pull)] [lambda: G] [kappa: G] [M: G x TPB ints]
+    // layout: [cur: D x TPB doubles, aliased by the spin words] [LsStage x warps] [LsStagePull x warps] [lambda] [kappa] [M]
     unsigned char *sp = ls_smem;
     double *cur_all = reinterpret_cast<double *>(sp);
     sp += sizeof(double) * QA_LS_D * QA_LS_TPB;
     LsStage *stages = reinterpret_cast<LsStage *>(sp);
     sp += sizeof(LsStage) * QA_LS_WPB;
     LsStagePull *pstages = reinterpret_cast<LsStagePull *>(sp);
-    if (VARIANT == 1) sp += sizeof(LsStagePull) * QA_LS_WPB;
-    uint32_t *words_all = reinterpret_cast<uint32_t *>(sp);
-    if (VARIANT == 1) sp += sizeof(uint32_t) * QA_LS_CAPW * QA_LS_TPB;
+    sp += sizeof(LsStagePull) * QA_LS_WPB;
+    uint32_t *words_all = reinterpret_cast<uint32_t *>(cur_all);
     double *lam_sh = reinterpret_cast<double *>(sp);
     sp += sizeof(double) * P.max_groups;
     long long *kap_sh = reinterpret_cast<long long *>(sp);
@@ -887,8 +890,8 @@ __global__ void __launch_bounds__(QA_LS_TPB, VARIANT == 0 ? 3 : 2) k_anneal_lock
         const bool active = r < D.reads;
         const unsigned long long sd = active ? P.seeds[D.read_base + r] : 1ull;
         unsigned long long s0 = sd ? sd : ~0ull, s1 = 0;
-        const LsCtx c = {D, P, r, active, fT, M_all + threadIdx.x, cur_all + threadIdx.x, stages[wib],
-                         pstages[VARIANT == 1 ? wib : 0], words_all + wib * (QA_LS_CAPW * 32) + lane, lam_sh, kap_sh};
+        const LsCtx c = {D, P, r, active, fT, M_all + threadIdx.x, cur_all + wib * (QA_LS_D * 32) + lane, stages[wib],
+                         pstages[wib], words_all + wib * (QA_LS_CAPW * 32) + lane, lam_sh, kap_sh};
         lockstep_tile<VARIANT, GROUPS>(c, s0, s1, st, P.error_flag);
     }
     // warp-reduce the per-lane counters
@@ -1570,7 +1573,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         const bool pull = kernel == QA_KERNEL_LOCKSTEP_PULL;
         const int tpp = (reads_per_problem + 31) / 32;
         const int64_t total_tiles = (int64_t)P * tpp;
-        const size_t smem = ls_smem_bytes(pull, std::max(M->ngroups, 1));
+        const size_t smem = ls_smem_bytes(std::max(M->ngroups, 1));
         const void *fn = nullptr;
         if (!pull) fn = groups ? (const void *)k_anneal_lockstep<0, true> : (const void *)k_anneal_lockstep<0, false>;
         else fn = groups ? (const void *)k_anneal_lockstep<1, true> : (const void *)k_anneal_lockstep<1, false>;
@@ -1601,11 +1604,9 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
                 A.fT_scratch = (double *)ctx->fT.p;
             }
         }
-        if (pull) {
-            rc = build_word_tables(M);
-            if (rc) return rc;
-            QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
-        }
+        rc = build_word_tables(M);  // field evaluation from spins (init pass of push, pull variant) runs on these
+        if (rc) return rc;
+        QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
         A.fT_stride = fT_stride;
         A.tiles_per_problem = tpp;
         A.total_tiles = total_tiles;
