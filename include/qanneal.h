@@ -56,6 +56,8 @@ extern "C" {
 #define QA_KERNEL_WARP_PER_READ 1  /* one warp per read: any read count, stream seeding */
 #define QA_KERNEL_LOCKSTEP_PUSH 2  /* one warp per 32 reads, read-interleaved fields: many reads (>= ~10^4) */
 #define QA_KERNEL_LOCKSTEP_PULL 3  /* kernel behind QA_MODE_THROUGHPUT (not selectable in reference mode) */
+#define QA_KERNEL_REPLAY 4         /* 32 reads per warp, deferred exact neighbour updates replayed at the visit; coupling
+                                      slabs TMA-staged per CTA.  Sparse models; falls back to _LOCKSTEP_PUSH otherwise */
 
 #define QA_MAX_GROUPS 64
 
@@ -89,8 +91,10 @@ int qa_device_count(void);
 int qa_ctx_create(int device_id, qa_ctx **out);
 int qa_ctx_destroy(qa_ctx *ctx);
 int qa_ctx_synchronize(qa_ctx *ctx);
-/* choose the reference-mode annealing kernel (QA_KERNEL_AUTO / _WARP_PER_READ / _LOCKSTEP_PUSH) */
+/* choose the reference-mode annealing kernel (QA_KERNEL_AUTO / _WARP_PER_READ / _LOCKSTEP_PUSH / _REPLAY) */
 int qa_ctx_set_kernel(qa_ctx *ctx, int kernel);
+/* QA_KERNEL_* the last sampling call of this context actually ran on (after automatic selection / fall-back) */
+int qa_ctx_last_kernel(qa_ctx *ctx);
 /* number of reads the annealing kernel keeps resident at once (one warp per read) */
 int qa_ctx_resident_reads(qa_ctx *ctx);
 

@@ -23,6 +23,8 @@ QA_MODE_THROUGHPUT = 1
 QA_KERNEL_AUTO = 0
 QA_KERNEL_WARP_PER_READ = 1
 QA_KERNEL_LOCKSTEP_PUSH = 2
+QA_KERNEL_LOCKSTEP_PULL = 3
+QA_KERNEL_REPLAY = 4
 QA_MAX_GROUPS = 64
 
 ERROR_NAMES = {
@@ -82,6 +84,7 @@ SIGNATURES = {
     "qa_ctx_synchronize": (C.c_int, [_p]),
     "qa_ctx_set_kernel": (C.c_int, [_p, C.c_int]),
     "qa_ctx_resident_reads": (C.c_int, [_p]),
+    "qa_ctx_last_kernel": (C.c_int, [_p]),
     "qa_model_from_ising": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p, C.POINTER(_p)]),
     "qa_model_set_groups": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
     "qa_model_num_variables": (C.c_int, [_p]),

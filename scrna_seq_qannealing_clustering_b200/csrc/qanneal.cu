@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -87,6 +88,9 @@ struct ProblemDesc {
     const int32_t *bw_ptr;      // [nblk + 1], this problem's first block at index 0 (values are global offsets)
     const int32_t *bw_words;    // global array
     const unsigned short *ent_slot; // indexed like col: slot | (bit << 8)
+    // coupling slabs of the replay kernel (null until built): one {RpHdr, RpEntry[]} per block of 16 variables
+    const unsigned char *rp_slabs;  // global slab storage
+    const uint32_t *rp_off;         // [nblk + 1] slab offsets of this problem in 16-byte units
 };
 
 struct AnnealParams {
@@ -114,6 +118,12 @@ struct AnnealParams {
     int32_t tiles_per_problem;
     int32_t max_groups;          // stride of the per-thread group counters in shared memory
     int64_t total_tiles;
+    // replay kernel (one CTA = `warps` consecutive 32-read tiles of one problem)
+    void *sf_scratch;            // [slots][sf_stride] {S,F} words, read-interleaved (uint2)
+    int64_t sf_stride;           // nch_max * 32
+    int64_t groups_per_problem;  // ceil(tiles_per_problem / warps per CTA)
+    int64_t total_items;         // num_problems * groups_per_problem
+    int32_t switch_permille;     // replay -> push hand-over: CTA-wide acceptance of a sweep below this many per mille
 };
 
 enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
@@ -908,6 +918,8 @@ __global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P
     }
 }
 
+#include "replay.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // energies: neal get_state_energy(), one thread per read, reads on lanes (coalesced packedT loads)
 // ------------------------------------------------------------------------------------------------
@@ -1188,8 +1200,11 @@ struct qa_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf f, spw, fT, states, energies, seeds, betas, packed, misc, cubtmp;
+    DevBuf f, spw, fT, sf, states, energies, seeds, betas, packed, misc, cubtmp;
     int kernel = 0;  // QA_KERNEL_*
+    int replay_switch_permille = 20;  // replay -> push hand-over threshold (QA_REPLAY_SWITCH_PERMILLE overrides)
+    int replay_warps = 0;             // warps per CTA of the replay kernel (0: automatic; QA_REPLAY_WARPS overrides)
+    int last_kernel = 0;              // QA_KERNEL_* the last sampling call ran on
     unsigned long long *d_stats = nullptr;  // QA_NSTAT counters + 1 read counter
     int *d_flag = nullptr;
     double *d_best_e = nullptr;
@@ -1221,6 +1236,10 @@ struct qa_model {
     int32_t *bw_ptr = nullptr, *bw_words = nullptr;
     unsigned short *ent_slot = nullptr;
     bool tables_built = false;
+    // coupling slabs of the replay kernel (built on first use; rp_ok = the model fits the slab format)
+    unsigned char *rp_slabs = nullptr;
+    uint32_t *rp_off = nullptr;
+    bool rp_built = false, rp_ok = false;
 };
 
 namespace {
@@ -1349,6 +1368,7 @@ int finalize_descs(qa_model *M) {
         D.w = M->w + c0;
         D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
         D.bw_ptr = nullptr; D.bw_words = nullptr; D.ent_slot = nullptr;
+        D.rp_slabs = nullptr; D.rp_off = nullptr;
         M->n_max = std::max(M->n_max, D.n);
     }
     M->nch_max = (M->n_max + 31) / 32;
@@ -1450,6 +1470,137 @@ int build_word_tables(qa_model *M) {
     return QA_OK;
 }
 
+// Coupling slabs of the replay kernel (replay.cuh): per block of RP_D variables one contiguous {RpHdr, RpEntry[]} record
+// with the rows in REPLAY order -- neighbours u > v ascending, then u < v ascending (stable, so duplicate couplers keep their
+// adjacency order) -- 2J premultiplied, and the slot / bit of the neighbour's spin word.  Built once per model on the host
+// from the device-built CSR (a setup step, O(entries)).  Models that do not fit the format (a block with more than RP_CAP
+// entries or more than RP_SLOTS-1 foreign spin words, i.e. dense models) leave rp_ok false and run on the other kernels.
+int build_replay_tables(qa_model *M) {
+    if (M->rp_built) return QA_OK;
+    qa_ctx *ctx = M->ctx;
+    M->rp_built = true;
+    M->rp_ok = false;
+    const int64_t entries = 2 * M->m_total;
+    const int64_t rows_alloc = M->n_total + 64 + 1;
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> rowptr(rows_alloc), col(std::max<int64_t>(entries, 1));
+    std::vector<double> val(std::max<int64_t>(entries, 1));
+    QA_CUDA(cudaMemcpy(rowptr.data(), M->rowptr, rows_alloc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (entries) {
+        QA_CUDA(cudaMemcpy(col.data(), M->col, entries * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        QA_CUDA(cudaMemcpy(val.data(), M->val, entries * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::vector<int32_t> hg, hc;
+    if (M->ngroups > 0) {
+        const int64_t npad = (int64_t)M->descs[0].nch * 32;
+        hg.resize(npad);
+        hc.resize(npad);
+        QA_CUDA(cudaMemcpy(hg.data(), M->grp, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        QA_CUDA(cudaMemcpy(hc.data(), M->coef, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint32_t> off;
+    std::vector<unsigned char> slabs;
+    std::vector<int64_t> blk_base(M->num_problems, 0);
+    std::vector<int32_t> stamp, slot_of;
+    std::vector<std::pair<int32_t, double>> later, earlier;
+    std::vector<RpEntry> E;
+    for (int p = 0; p < M->num_problems; ++p) {
+        const int64_t v_off = M->var_off[p];
+        const int n = (int)(M->var_off[p + 1] - v_off);
+        if (n == 0) return QA_OK;
+        const int nch = (n + 31) / 32;
+        const int nblk = nch * (32 / RP_D);
+        blk_base[p] = (int64_t)off.size();
+        stamp.assign(nch, -1);
+        slot_of.assign(nch, 0);
+        for (int b = 0; b < nblk; ++b) {
+            const int v0 = b * RP_D;
+            const int own = v0 >> 5;
+            RpHdr H;
+            memset(&H, 0, sizeof(H));
+            E.clear();
+            int nbw = 0;
+            for (int i = 0; i < RP_D; ++i) {
+                const int v = v0 + i;
+                const size_t start = E.size();
+                H.row[i] = (uint32_t)start | ((uint32_t)start << 16);
+                H.ga[i] = 255;
+                H.nlater[i] = 0;
+                H.deg[i] = 0;
+                if (v >= n) continue;
+                if (M->ngroups > 0 && hg[v] >= 0) {
+                    if (hc[v] >= (1 << 23) || hc[v] <= -(1 << 23)) return QA_OK;  // coefficient does not fit the packed form
+                    H.ga[i] = (int32_t)((uint32_t)hg[v] | ((uint32_t)hc[v] << 8));
+                }
+                later.clear();
+                earlier.clear();
+                for (int64_t e = rowptr[v_off + v]; e < rowptr[v_off + v + 1]; ++e) {
+                    if (col[e] > v) later.emplace_back(col[e], val[e]);
+                    else earlier.emplace_back(col[e], val[e]);
+                }
+                auto by_index = [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b) { return a.first < b.first; };
+                std::stable_sort(later.begin(), later.end(), by_index);
+                std::stable_sort(earlier.begin(), earlier.end(), by_index);
+                const size_t deg = later.size() + earlier.size();
+                const size_t padded = (deg + 3) & ~(size_t)3;
+                if (start + padded > (size_t)RP_CAP) return QA_OK;
+                H.nlater[i] = (uint16_t)later.size();
+                H.deg[i] = (uint16_t)deg;
+                for (int part = 0; part < 2; ++part) {
+                    for (const auto &nb : (part == 0 ? later : earlier)) {
+                        const int j = nb.first;
+                        const int wj = j >> 5;
+                        int slot = 0;
+                        if (wj != own) {
+                            if (stamp[wj] != b) {
+                                if (nbw >= RP_MAXBW) return QA_OK;
+                                stamp[wj] = b;
+                                slot_of[wj] = nbw + 1;
+                                H.bw[nbw++] = wj;
+                            }
+                            slot = slot_of[wj];
+                        }
+                        RpEntry en;
+                        en.J2 = 2.0 * nb.second;
+                        en.j = j;
+                        en.B = (uint32_t)(31 - (j & 31)) | ((uint32_t)slot << 8) | ((j / RP_D) == b ? 0x8000u : 0u);
+                        E.push_back(en);
+                    }
+                }
+                for (size_t k = deg; k < padded; ++k) {   // never flagged: the all-zero slot
+                    RpEntry en;
+                    en.J2 = 0.0;
+                    en.j = v;
+                    en.B = (uint32_t)(RP_SLOTS - 1) << 8;
+                    E.push_back(en);
+                }
+                H.row[i] = (uint32_t)start | ((uint32_t)(start + padded) << 16);
+            }
+            H.nent = (int32_t)E.size();
+            H.nbw = nbw;
+            if (slabs.size() / 16 > 0xfffffff0ull) return QA_OK;
+            off.push_back((uint32_t)(slabs.size() / 16));
+            const unsigned char *hp = reinterpret_cast<const unsigned char *>(&H);
+            slabs.insert(slabs.end(), hp, hp + sizeof(H));
+            const unsigned char *ep = reinterpret_cast<const unsigned char *>(E.data());
+            slabs.insert(slabs.end(), ep, ep + E.size() * sizeof(RpEntry));
+        }
+    }
+    off.push_back((uint32_t)(slabs.size() / 16));
+    if (slabs.empty()) return QA_OK;
+    QA_CUDA(cudaMalloc((void **)&M->rp_slabs, slabs.size()));
+    QA_CUDA(cudaMalloc((void **)&M->rp_off, off.size() * sizeof(uint32_t)));
+    QA_CUDA(cudaMemcpyAsync(M->rp_slabs, slabs.data(), slabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(M->rp_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < M->num_problems; ++p) {
+        M->descs[p].rp_slabs = M->rp_slabs;
+        M->descs[p].rp_off = M->rp_off + blk_base[p];
+    }
+    M->rp_ok = true;
+    return QA_OK;
+}
+
 struct RunBuffers {
     int8_t *d_states = nullptr;
     double *d_energies = nullptr;
@@ -1504,7 +1655,21 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         kernel = QA_KERNEL_LOCKSTEP_PUSH;
     if (kernel == QA_KERNEL_LOCKSTEP_PULL && seed_mode != QA_SEED_PER_READ)
         return fail(QA_ERR_ARG, "throughput mode needs per-read seeding");
+    // replay kernel (deferred exact updates): sparse models whose blocks fit the slab format; explicit choice, or
+    // automatic wherever the lockstep push kernel would have been taken
+    if (mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ &&
+        (ctx->kernel == QA_KERNEL_REPLAY || (ctx->kernel == QA_KERNEL_AUTO && kernel == QA_KERNEL_LOCKSTEP_PUSH))) {
+        rc = build_replay_tables(M);
+        if (rc) return rc;
+        if (M->rp_ok) {
+            kernel = QA_KERNEL_REPLAY;
+            QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
+        } else if (ctx->kernel == QA_KERNEL_REPLAY) {
+            kernel = QA_KERNEL_LOCKSTEP_PUSH;  // dense model: the slab format does not apply
+        }
+    }
 
+    ctx->last_kernel = kernel;
     QA_CUDA(cudaMemsetAsync(ctx->d_stats, 0, (QA_NSTAT + 1) * sizeof(unsigned long long), ctx->stream));
     QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
 
@@ -1568,6 +1733,57 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
                 if (interrupt(iuser)) { interrupted = true; break; }
             }
         }
+    } else if (kernel == QA_KERNEL_REPLAY) {
+        // replay: one CTA = `nw` consecutive 32-read tiles of one problem, coupling slabs shared through a TMA ring
+        const int tpp = (reads_per_problem + 31) / 32;
+        int nw = ctx->replay_warps;
+        if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {
+            nw = 1;
+            while (nw < 8 && nw < tpp) nw *= 2;
+        }
+        const int64_t gpp = (tpp + nw - 1) / nw;
+        const int64_t total_items = (int64_t)P * gpp;
+        const int mg = std::max(M->ngroups, 1);
+        const size_t smem = rp_smem_bytes(nw, mg);
+        const void *fn = groups ? (const void *)k_anneal_replay<true> : (const void *)k_anneal_replay<false>;
+        QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int bps = 0;
+        QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, nw * 32, smem, cudaOccupancyDefault));
+        if (bps < 1) return fail(QA_ERR_CUDA, "replay kernel does not fit on an SM");
+        int64_t grid = std::min<int64_t>((int64_t)bps * ctx->num_sms, total_items);
+        const int64_t fT_stride = (int64_t)M->nch_max * 32 * 32;
+        const int64_t sf_stride = (int64_t)M->nch_max * 32;
+        {
+            size_t free_b = 0, total_b = 0;
+            QA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t per_slot = (size_t)fT_stride * sizeof(double) + (size_t)sf_stride * sizeof(uint2);
+            const size_t budget = (size_t)((double)(free_b + ctx->fT.bytes + ctx->sf.bytes) * 0.9);
+            const int64_t max_slots = (int64_t)(budget / per_slot);
+            if (max_slots < nw) return fail(QA_ERR_CUDA, "not enough device memory for one CTA of local fields");
+            if (grid * nw > max_slots) grid = max_slots / nw;
+            rc = ensure(ctx->fT, (size_t)grid * nw * fT_stride * sizeof(double));
+            if (!rc) rc = ensure(ctx->sf, (size_t)grid * nw * sf_stride * sizeof(uint2));
+            if (rc) return rc;
+        }
+        A.fT_scratch = (double *)ctx->fT.p;
+        A.fT_stride = fT_stride;
+        A.sf_scratch = ctx->sf.p;
+        A.sf_stride = sf_stride;
+        A.tiles_per_problem = tpp;
+        A.groups_per_problem = gpp;
+        A.total_items = total_items;
+        A.max_groups = mg;
+        A.switch_permille = ctx->replay_switch_permille;
+        A.read_begin = 0;
+        A.read_end = total_reads;
+        QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+        QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
+        void *args[] = {&A};
+        QA_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(nw * 32), args, smem, ctx->stream));
+        QA_CUDA(cudaGetLastError());
+        ctx->launches++;
+        if (st) st->anneal_launches++;
+        done = total_reads;
     } else {
         // lockstep: one warp = 32 reads of one problem
         const bool pull = kernel == QA_KERNEL_LOCKSTEP_PULL;
@@ -1765,6 +1981,8 @@ int qa_ctx_create(int device_id, qa_ctx **out) {
     cudaDeviceProp prop;
     QA_CUDA(cudaGetDeviceProperties(&prop, device_id));
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char *e = getenv("QA_REPLAY_SWITCH_PERMILLE")) ctx->replay_switch_permille = atoi(e);  // development knobs
+    if (const char *e = getenv("QA_REPLAY_WARPS")) ctx->replay_warps = atoi(e);
     QA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) QA_CUDA(cudaEventCreate(&ev));
     QA_CUDA(cudaMalloc((void **)&ctx->d_stats, (QA_NSTAT + 1) * sizeof(unsigned long long)));
@@ -1779,7 +1997,7 @@ int qa_ctx_destroy(qa_ctx *ctx) {
     if (!ctx) return QA_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    release(ctx->f); release(ctx->spw); release(ctx->fT); release(ctx->states); release(ctx->energies); release(ctx->seeds);
+    release(ctx->f); release(ctx->spw); release(ctx->fT); release(ctx->sf); release(ctx->states); release(ctx->energies); release(ctx->seeds);
     release(ctx->betas); release(ctx->packed); release(ctx->misc); release(ctx->cubtmp);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -1799,10 +2017,16 @@ int qa_ctx_synchronize(qa_ctx *ctx) {
 
 int qa_ctx_set_kernel(qa_ctx *ctx, int kernel) {
     if (!ctx) return fail(QA_ERR_ARG, "null context");
-    if (kernel != QA_KERNEL_AUTO && kernel != QA_KERNEL_WARP_PER_READ && kernel != QA_KERNEL_LOCKSTEP_PUSH)
-        return fail(QA_ERR_ARG, "kernel must be QA_KERNEL_AUTO, QA_KERNEL_WARP_PER_READ or QA_KERNEL_LOCKSTEP_PUSH");
+    if (kernel != QA_KERNEL_AUTO && kernel != QA_KERNEL_WARP_PER_READ && kernel != QA_KERNEL_LOCKSTEP_PUSH &&
+        kernel != QA_KERNEL_REPLAY)
+        return fail(QA_ERR_ARG, "kernel must be QA_KERNEL_AUTO, _WARP_PER_READ, _LOCKSTEP_PUSH or _REPLAY");
     ctx->kernel = kernel;
     return QA_OK;
+}
+
+int qa_ctx_last_kernel(qa_ctx *ctx) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    return ctx->last_kernel;
 }
 
 int qa_ctx_resident_reads(qa_ctx *ctx) {
@@ -1835,6 +2059,12 @@ int qa_model_set_groups(qa_model *M, int32_t ngroups, const int32_t *grp, const 
     if (M->lambda) { cudaFree(M->lambda); M->lambda = nullptr; }
     if (M->kappa) { cudaFree(M->kappa); M->kappa = nullptr; }
     M->ngroups = ngroups;
+    if (M->rp_slabs) { cudaFree(M->rp_slabs); M->rp_slabs = nullptr; }   // the slabs carry the group metadata
+    if (M->rp_off) { cudaFree(M->rp_off); M->rp_off = nullptr; }
+    M->rp_built = false;
+    M->rp_ok = false;
+    M->descs[0].rp_slabs = nullptr;
+    M->descs[0].rp_off = nullptr;
     ProblemDesc &D = M->descs[0];
     D.ngroups = ngroups;
     D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
@@ -1895,7 +2125,7 @@ int qa_model_destroy(qa_model *M) {
     cudaSetDevice(M->ctx->device);
     cudaStreamSynchronize(M->ctx->stream);
     void *ptrs[] = {M->h, M->starts, M->ends, M->w, M->rowptr, M->col, M->val, M->grp, M->coef, M->lambda, M->kappa, M->d_descs,
-                    M->bw_ptr, M->bw_words, M->ent_slot};
+                    M->bw_ptr, M->bw_words, M->ent_slot, M->rp_slabs, M->rp_off};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete M;
     return QA_OK;

@@ -1,0 +1,532 @@
+// replay.cuh -- k_anneal_replay: bit-exact reference-order annealing with DEFERRED neighbour updates.
+// Included by qanneal.cu (needs ProblemDesc, AnnealParams, LaneStats, ls_accept, red_add_f64_if).
+//
+// neal (cpu_sa.cpp simulated_annealing_run) pushes every accepted flip of u into the flip energies of
+// all neighbours j at once.  On a GPU with 32 reads per warp that is a random 8-byte read-modify-write per (flip, neighbour)
+// on a field matrix far larger than L2; measured on B200 (tools/ubench_update.cu) the memory system tops out at
+// 1.5-2.8e10 attempts/s for every acceptance rate >= 5 % -- the lockstep push kernel already sits at that ceiling.
+//
+// This kernel keeps the SAME arithmetic but changes when it happens.  Per read it stores
+//     f[v]  the local field h_v + sum_j J_vj s_j as of the LAST VISIT of v      (fp64, read-interleaved f[v][lane])
+//     S[v]  the spin, F[v] "v flipped at its last visit"                           (bit-packed, {S,F}[word][lane])
+// Between two visits of v every neighbour u is visited exactly once, so the updates neal would have pushed into f[v] are
+//     + 2 s_u J_uv   for the flagged neighbours u > v (flipped later in the previous sweep), ascending u, then
+//     + 2 s_u J_uv   for the flagged neighbours u < v (flipped earlier in this sweep),       ascending u
+// -- the same fp64 additions in the same order (s_u is the spin after the flip; a neighbour cannot flip twice in that
+// window).  Replaying them at the visit gives bit-identical fields, decisions, RNG draws and final states, but the memory
+// traffic becomes sequential and fully coalesced: 8 B of field per attempt (+8 B when it changed) plus the {S,F} words of
+// the neighbour cells, instead of 16 B x 4 (sector granularity) per (flip, neighbour).
+// When flips become rare the cost balance inverts (a replay touches every neighbour of every variable, a push only the
+// neighbours of accepted flips), so once the CTA-wide acceptance of a sweep drops below P.switch_permille the tile runs one
+// catch-up pass (pending u > v updates only) and finishes the schedule pushing, as neal does.  Both forms are exact, so
+// the hand-over point does not influence the result.
+//
+// Coupling slabs: for every block of RP_D variables the host builds one contiguous slab {RpHdr, RpEntry[]} (replay order,
+// 2J premultiplied, slot/bit of the neighbour's spin word).  All warps of a CTA walk the blocks together; slabs are brought
+// into a 3-stage shared-memory ring by one elected thread with cp.async.bulk (TMA 1-D) completing on mbarriers, and
+// released by one mbarrier arrive per warp -- no __syncthreads in the sweep.
+#pragma once
+
+constexpr int RP_D = 16;         // variables per block
+constexpr int RP_CAP = 448;      // entries per slab (rows padded to multiples of 4)
+constexpr int RP_SLOTS = 32;     // spin-word slots per warp: slot 0 = the block's own word, slot 31 = all-zero (padding entries)
+constexpr int RP_MAXBW = 30;     // foreign spin words per block
+constexpr int RP_STAGES = 3;
+constexpr int RP_WARP_BYTES = RP_SLOTS * 32 * 8;  // 8 KB per warp: {~S,F}[slot][lane]; the push phase stages fields here
+
+struct RpHdr {
+    int32_t nent;            // entries in this slab (with padding)
+    int32_t nbw;             // distinct neighbour words other than the block's own word
+    uint32_t row[16];        // entry range of variable i: start | (padded end << 16)
+    uint16_t nlater[16];     // leading entries of row i that refer to later variables (u > v)
+    uint16_t deg[16];        // true degree of row i (entries [start, start + deg) are real, the rest padding)
+    int32_t ga[16];          // group (low byte, 255: none) | coefficient << 8
+    int32_t bw[RP_MAXBW];    // neighbour word indices, slot s+1 holds word bw[s]
+};
+static_assert(sizeof(RpHdr) == 320, "slab header layout");
+constexpr uint32_t RP_H_NBW = 4, RP_H_ROW = 8, RP_H_NLATER = 72, RP_H_DEG = 104, RP_H_GA = 136, RP_H_BW = 200;
+struct __align__(16) RpEntry {
+    double J2;     // 2 * J (padding entries: 0)
+    int32_t j;     // neighbour (local variable index)
+    uint32_t B;    // bits 0-4: 31 - (j & 31); bits 8-12: slot; bit 15: neighbour inside the same block
+};
+constexpr int RP_STAGE_BYTES = (int)sizeof(RpHdr) + RP_CAP * (int)sizeof(RpEntry);
+static_assert(RP_STAGE_BYTES % 16 == 0, "stage alignment");
+
+// ---- mbarrier / TMA 1-D primitives -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared-memory accesses by explicit address (volatile: kept in program order among themselves and after the barrier waits)
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+    int4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y));
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
+}
+// f += d on the lanes whose flag word has its top bit set (one predicated DADD: the only serial dependence of a replay)
+__device__ __forceinline__ void add_f64_if_neg(double &f, double d, uint32_t t) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(f) : "d"(d), "r"(t));
+}
+
+struct RpCtx {
+    // ring (CTA-shared)
+    uint32_t full_s, empty_s, stage_s;   // shared addresses: full[0], empty[0] (8 B apart), stage 0
+    const unsigned char *slabs;          // global slab storage
+    const uint32_t *off;                 // [nblk + 1] slab offsets of this problem, in 16-byte units
+    uint32_t stage, phase;               // stage / phase of the next block to consume
+    // per lane
+    double *fT;                          // f[v][lane], this lane's column
+    uint2 *SF;                           // {S,F}[word][lane], this lane's column
+    uint32_t sfbase_s;                   // shared address of this lane's column in the warp's 8 KB-aligned region
+    int *Mcol;
+    int mstride;
+    const double *lam;
+    const long long *kap;
+    unsigned long long s0, s1;
+    LaneStats st;
+    bool active;
+    int n, nblk;
+};
+
+// thread 0 only: start the copy of block `blk` into the stage that follows the one being consumed
+__device__ __forceinline__ void rp_issue_next(const RpCtx &c, int blk) {
+    uint32_t st = c.stage + 1, ph = c.phase;
+    if (st == RP_STAGES) { st = 0; ph ^= 1u; }
+    mbar_wait(c.empty_s + 8u * st, ph ^ 1u);     // every warp has released the previous use of that stage
+    const uint32_t o0 = __ldg(c.off + blk), o1 = __ldg(c.off + blk + 1);
+    const uint32_t bytes = (o1 - o0) * 16u;
+    mbar_expect_tx(c.full_s + 8u * st, bytes);
+    tma_load_1d(c.stage_s + st * (uint32_t)RP_STAGE_BYTES, c.slabs + (size_t)o0 * 16u, bytes, c.full_s + 8u * st);
+}
+// thread 0 only: the first block of a work item goes into the stage about to be consumed
+__device__ __forceinline__ void rp_issue_first(const RpCtx &c) {
+    mbar_wait(c.empty_s + 8u * c.stage, c.phase ^ 1u);
+    const uint32_t o0 = __ldg(c.off), o1 = __ldg(c.off + 1);
+    const uint32_t bytes = (o1 - o0) * 16u;
+    mbar_expect_tx(c.full_s + 8u * c.stage, bytes);
+    tma_load_1d(c.stage_s + c.stage * (uint32_t)RP_STAGE_BYTES, c.slabs + (size_t)o0 * 16u, bytes, c.full_s + 8u * c.stage);
+}
+
+// One pass over all blocks.  MODE 0: replay sweep (pull).  MODE 1: catch-up (pending later-neighbour updates only, no
+// decisions).  MODE 2: push sweep (neal's eager form).  Returns the number of accepted flips of the warp.
+template <int MODE, bool GROUPS>
+__device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
+    const int lane = threadIdx.x & 31;
+    const double thr = 44.36142 / beta;
+    const int n = c.n, nblk = c.nblk;
+    double *const fT = c.fT;
+    uint2 *const SF = c.SF;
+    const uint32_t sfb = c.sfbase_s;
+    const bool active = c.active;
+    unsigned sweep_acc = 0;
+    uint32_t S = 0xffffffffu, F = 0u, S0 = 0xffffffffu, F0 = 0u;
+
+    for (int blk = 0; blk < nblk; ++blk) {
+        if (threadIdx.x == 0) {
+            const bool last = blk == nblk - 1;
+            if (!last || has_next_pass) rp_issue_next(c, last ? 0 : blk + 1);
+        }
+        __syncwarp();
+        mbar_wait(c.full_s + 8u * c.stage, c.phase);
+        const uint32_t hdr = c.stage_s + c.stage * (uint32_t)RP_STAGE_BYTES;   // shared address of the slab
+        const uint32_t ent = hdr + (uint32_t)sizeof(RpHdr);
+        const int v0 = blk * RP_D;
+        const int wi = v0 >> 5;
+        const int sub = v0 & 31;
+        double *const fB = fT + (int64_t)v0 * 32;
+        if (sub == 0) {
+            const uint2 own = __ldcg(SF + (int64_t)wi * 32);
+            S = own.x; F = own.y; S0 = S; F0 = F;
+        }
+        {   // run-ahead of the field rows two blocks on (L2 prefetch, 128 B per lane = 16 rows)
+            int pv = v0 + 2 * RP_D;
+            if (pv >= nblk * RP_D) pv -= nblk * RP_D;
+            const char *pa = reinterpret_cast<const char *>(fT - lane + (int64_t)pv * 32) + lane * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        }
+        bool blk_dirty = false;
+        if (MODE <= 1) {
+            // this lane's copy of every spin/flag word the block refers to (~S so that a set top bit means "spin down")
+            const int nbw = (int)lds_u32(hdr + RP_H_NBW);
+            for (int s = 0; s < nbw; s += 8) {
+                uint2 t[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (s + q < nbw) t[q] = __ldcg(SF + (int64_t)lds_u32(hdr + RP_H_BW + 4u * (uint32_t)(s + q)) * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (s + q < nbw) sts_u2(sfb + (uint32_t)(s + q + 1) * 256u, ~t[q].x, t[q].y);
+            }
+            sts_u2(sfb, ~S, F);
+        } else {
+            double t[RP_D];
+#pragma unroll
+            for (int i = 0; i < RP_D; ++i) t[i] = __ldcg(fB + i * 32);
+#pragma unroll
+            for (int i = 0; i < RP_D; ++i) sts_f64(sfb + (uint32_t)i * 256u, t[i]);
+        }
+        double f_next = 0.0;
+        if (MODE <= 1) f_next = __ldcg(fB);
+        const int ilim = min(RP_D, n - v0);   // uniform: padding variables are not visited
+
+        for (int i = 0; i < ilim; ++i) {
+            const uint32_t rw = lds_u32(hdr + RP_H_ROW + 4u * (uint32_t)i);
+            const uint32_t a0 = ent + (rw & 0xffffu) * 16u;
+            const uint32_t bit = 1u << (sub + i);
+            const bool up = (S & bit) != 0u;
+            double fv;
+            if (MODE <= 1) {
+                fv = f_next;
+                if (i + 1 < RP_D) f_next = __ldcg(fB + (i + 1) * 32);
+                const double f0 = fv;
+                if (MODE == 0) {
+                    // four entries per round: table entries first, then the lane's {~S,F} words, then the ordered additions
+                    // (rows are padded to a multiple of four with entries that point at the all-zero slot: never flagged)
+                    const uint32_t a1 = ent + (rw >> 16) * 16u;
+                    for (uint32_t a = a0; a < a1; a += 64u) {
+                        int4 q[4];
+                        uint2 sf[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) q[k] = lds_v4(a + 16u * k);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sf[k] = lds_u2(((uint32_t)q[k].w & 0x1F00u) | sfb);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t B = (uint32_t)q[k].w;
+                            const uint32_t sg = __funnelshift_l(0u, sf[k].x, B) & 0x80000000u;   // spin down: add -2J
+                            add_f64_if_neg(fv, __hiloint2double(q[k].y ^ (int)sg, q[k].x), __funnelshift_l(0u, sf[k].y, B));
+                        }
+                    }
+                } else {
+                    const uint32_t a1 = a0 + lds_u16(hdr + RP_H_NLATER + 2u * (uint32_t)i) * 16u;
+                    for (uint32_t a = a0; a < a1; a += 16u) {
+                        const int4 q = lds_v4(a);
+                        const uint2 sf = lds_u2(((uint32_t)q.w & 0x1F00u) | sfb);
+                        const uint32_t sg = __funnelshift_l(0u, sf.x, (uint32_t)q.w) & 0x80000000u;
+                        add_f64_if_neg(fv, __hiloint2double(q.y ^ (int)sg, q.x), __funnelshift_l(0u, sf.y, (uint32_t)q.w));
+                    }
+                }
+                if (fv != f0) __stcg(fB + i * 32, fv);
+                if (MODE == 1) continue;
+            } else {
+                fv = lds_f64(sfb + (uint32_t)i * 256u);
+            }
+            double dE = up ? -2.0 * fv : 2.0 * fv;
+            int g = 255, a = 0;
+            if (GROUPS) {
+                const int ga = (int)lds_u32(hdr + RP_H_GA + 4u * (uint32_t)i);
+                g = ga & 255;
+                if (g != 255) {
+                    a = ga >> 8;
+                    const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)c.Mcol[g * c.mstride] + c.kap[g]));
+                    dE = dE + c.lam[g] * (double)t;
+                }
+            }
+            const bool cand = active && !(dE >= thr);
+            bool acc = false;
+            if (__any_sync(FULL_MASK, cand)) {
+                if (cand) c.st.cand++;
+                acc = ls_accept(dE, cand, beta, c.s0, c.s1, c.st);
+            }
+            if (MODE == 0) {
+                // F[v] := accepted (also when nothing was accepted: the flag of the previous visit must be cleared)
+                F = acc ? (F | bit) : (F & ~bit);
+                if (acc) S ^= bit;
+                sts_u2(sfb, ~S, F);
+                if (acc) {
+                    c.st.acc++;
+                    c.st.nbr += (unsigned long long)lds_u16(hdr + RP_H_DEG + 2u * (uint32_t)i);
+                    if (GROUPS) {
+                        if (g != 255) c.Mcol[g * c.mstride] -= 2 * a * (up ? 1 : -1);
+                    }
+                }
+                sweep_acc += __popc(__ballot_sync(FULL_MASK, acc));
+            } else {
+                const unsigned accm = __ballot_sync(FULL_MASK, acc);
+                if (accm == 0u) continue;
+                sweep_acc += __popc(accm);
+                const int sgn = up ? (int)0x80000000u : 0;   // f[j] += -2 s_v J
+                const uint32_t deg = lds_u16(hdr + RP_H_DEG + 2u * (uint32_t)i);
+                const uint32_t a1 = a0 + deg * 16u;
+#pragma unroll 4
+                for (uint32_t ad = a0; ad < a1; ad += 16u) {
+                    const int4 q = lds_v4(ad);
+                    const double d = __hiloint2double(q.y ^ sgn, q.x);
+                    if ((uint32_t)q.w & 0x8000u) {   // uniform: neighbour staged in this block
+                        const uint32_t ca = sfb + (((uint32_t)q.z & (uint32_t)(RP_D - 1)) << 8);
+                        if (acc) sts_f64(ca, lds_f64(ca) + d);
+                        blk_dirty = true;
+                    } else {
+                        red_add_f64_if(fT + (int64_t)q.z * 32, d, acc);
+                    }
+                }
+                if (acc) {
+                    S ^= bit;
+                    c.st.acc++;
+                    c.st.nbr += (unsigned long long)deg;
+                    if (GROUPS) {
+                        if (g != 255) c.Mcol[g * c.mstride] -= 2 * a * (up ? 1 : -1);
+                    }
+                }
+            }
+        }
+        if (MODE == 2) {
+            if (blk_dirty) {  // uniform: write the staged fields back (coalesced 256 B rows)
+#pragma unroll
+                for (int i = 0; i < RP_D; ++i) __stcg(fB + i * 32, lds_f64(sfb + (uint32_t)i * 256u));
+            }
+        }
+        if (MODE != 1 && sub + RP_D == 32) {
+            if (S != S0 || F != F0) __stcg(SF + (int64_t)wi * 32, make_uint2(S, F));
+        }
+        // release the stage: one arrive per warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.empty_s + 8u * c.stage);
+        if (++c.stage == RP_STAGES) { c.stage = 0; c.phase ^= 1u; }
+    }
+    return sweep_acc;
+}
+
+// local field of v in neal's get_flip_energy order (adjacency order), spins from the {S,F} scratch; loads batched by 8
+__device__ __forceinline__ double rp_field_direct(const ProblemDesc &D, const uint2 *SF, int v, int e0, int e1) {
+    double fv = __ldg(D.h + v);
+    for (int e = e0; e < e1; e += 8) {
+        int jq[8];
+        uint32_t wq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            jq[q] = __ldg(D.col + min(e + q, e1 - 1));
+            wq[q] = __ldcg(SF + (int64_t)(jq[q] >> 5) * 32).x;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (e + q < e1) {
+                const double J = __ldg(D.val + e + q);
+                fv += ((wq[q] >> (jq[q] & 31)) & 1u) ? J : -J;
+            }
+        }
+    }
+    return fv;
+}
+
+__host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups) {
+    size_t b = 8192;                                    // slack to align the warp regions to 8 KB
+    b += (size_t)nw * RP_WARP_BYTES;
+    b += (size_t)RP_STAGES * RP_STAGE_BYTES;
+    b += 8 * (2 * RP_STAGES) + 32;                      // mbarriers + CTA scratch
+    b += (sizeof(double) + sizeof(long long)) * (size_t)max_groups;
+    b += sizeof(int) * (size_t)max_groups * nw * 32;
+    return b;
+}
+
+template <bool GROUPS>
+__global__ void __launch_bounds__(256, 2) k_anneal_replay(AnnealParams P) {
+    extern __shared__ __align__(16) unsigned char rp_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int NW = blockDim.x >> 5;
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(rp_raw);
+    const uint32_t base_s = (raw_s + 8191u) & ~8191u;
+    unsigned char *base = rp_raw + (base_s - raw_s);
+    unsigned char *stages = base + (size_t)NW * RP_WARP_BYTES;
+    unsigned char *tail = stages + (size_t)RP_STAGES * RP_STAGE_BYTES;
+    const uint32_t bars_s = base_s + (uint32_t)NW * RP_WARP_BYTES + (uint32_t)RP_STAGES * RP_STAGE_BYTES;
+    long long *item_sh = reinterpret_cast<long long *>(tail + 8 * (2 * RP_STAGES));
+    unsigned *acc_sh = reinterpret_cast<unsigned *>(tail + 8 * (2 * RP_STAGES) + 8);   // [2]
+    double *lam_sh = reinterpret_cast<double *>(tail + 8 * (2 * RP_STAGES) + 32);
+    long long *kap_sh = reinterpret_cast<long long *>(lam_sh + P.max_groups);
+    int *M_all = reinterpret_cast<int *>(kap_sh + P.max_groups);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RP_STAGES; ++s) {
+            mbar_init(bars_s + 8u * s, 1);                     // full: the producer's arrive.expect_tx
+            mbar_init(bars_s + 8u * (RP_STAGES + s), NW);      // empty: one arrive per warp
+        }
+        acc_sh[0] = 0u;
+        acc_sh[1] = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (GROUPS) {  // groups exist only on single-problem models: one copy of lambda / kappa per block
+        const ProblemDesc &D0 = P.descs[0];
+        for (int g = threadIdx.x; g < D0.ngroups; g += blockDim.x) {
+            lam_sh[g] = D0.lambda[g];
+            kap_sh[g] = D0.kappa[g];
+        }
+    }
+    __syncthreads();
+
+    RpCtx c;
+    c.full_s = bars_s;
+    c.empty_s = bars_s + 8u * RP_STAGES;
+    c.stage_s = base_s + (uint32_t)NW * RP_WARP_BYTES;
+    c.stage = 0;
+    c.phase = 0;
+    c.sfbase_s = base_s + (uint32_t)wib * RP_WARP_BYTES + (uint32_t)lane * 8u;
+    sts_u2(c.sfbase_s + (uint32_t)(RP_SLOTS - 1) * 256u, 0u, 0u);   // the all-zero slot of the padding entries
+    c.Mcol = M_all + threadIdx.x;
+    c.mstride = (int)blockDim.x;
+    c.lam = lam_sh;
+    c.kap = kap_sh;
+    c.st = {0, 0, 0, 0, 0};
+    const int64_t slot = (int64_t)blockIdx.x * NW + wib;
+    c.fT = P.fT_scratch + slot * P.fT_stride + lane;
+    c.SF = reinterpret_cast<uint2 *>(P.sf_scratch) + slot * P.sf_stride + lane;
+    int acc_par = 0;
+
+    for (;;) {
+        if (threadIdx.x == 0) *item_sh = (long long)atomicAdd(P.counter, 1ull);
+        __syncthreads();
+        const int64_t item = *item_sh;
+        __syncthreads();
+        if (item >= P.total_items) break;
+        const int p = (int)(item / P.groups_per_problem);
+        const int64_t q = item % P.groups_per_problem;
+        const ProblemDesc D = P.descs[p];
+        const int64_t tile = q * NW + wib;
+        const int64_t r = tile * 32 + lane;
+        const bool active = r < D.reads;
+        const long long cta_reads = min((long long)NW * 32, (long long)D.reads - (long long)q * NW * 32);
+        c.active = active;
+        c.n = D.n;
+        c.nblk = D.nch * (32 / RP_D);
+        c.slabs = D.rp_slabs;
+        c.off = D.rp_off;
+        const long long total_sweeps = (long long)P.num_betas * P.sweeps_per_beta;
+        if (threadIdx.x == 0 && total_sweeps > 0) rp_issue_first(c);   // overlaps with the set-up below
+
+        const unsigned long long sd = active ? P.seeds[D.read_base + r] : 1ull;
+        c.s0 = sd ? sd : ~0ull;
+        c.s1 = 0;
+        const int n = D.n, nch = D.nch;
+        // ---- pack this read's +-1 bytes (padding lanes and padding variables are +1), clear the flags
+        for (int wi = 0; wi < nch; ++wi) {
+            uint32_t w = 0xffffffffu;
+            if (active) {
+                const int8_t *row = D.states + r * (int64_t)n + wi * 32;
+                const int lim = min(32, n - wi * 32);
+                for (int i = 0; i < lim; ++i) {
+                    const int s = row[i];
+                    if (s != 1 && s != -1) atomicExch(P.error_flag, QA_ERR_STATE);
+                    if (s < 0) w &= ~(1u << i);
+                }
+            }
+            __stcg(c.SF + (int64_t)wi * 32, make_uint2(w, 0u));
+        }
+        if (GROUPS) {
+            for (int g = 0; g < D.ngroups; ++g) c.Mcol[g * c.mstride] = 0;
+            for (int wi = 0; wi < nch; ++wi) {
+                const uint32_t w = __ldcg(c.SF + (int64_t)wi * 32).x;
+                for (int i = 0; i < 32; ++i) {
+                    const int v = wi * 32 + i;
+                    const int g = __ldg(D.grp + v);  // uniform
+                    if (g >= 0) {
+                        const int a = __ldg(D.coef + v);
+                        c.Mcol[g * c.mstride] += ((w >> i) & 1u) ? a : -a;
+                    }
+                }
+            }
+        }
+        // ---- local fields in neal's get_flip_energy order
+        {
+            int e0 = __ldg(D.rowptr);
+            for (int v = 0; v < n; ++v) {
+                const int e1 = __ldg(D.rowptr + v + 1);
+                __stcg(c.fT + (int64_t)v * 32, rp_field_direct(D, c.SF, v, e0, e1));
+                e0 = e1;
+            }
+        }
+        // ---- the schedule: replay sweeps while flips are frequent, then one catch-up pass and push sweeps
+        bool push = false;
+        long long done = 0;
+        for (int bi = 0; bi < P.num_betas; ++bi) {
+            const double beta = P.betas[bi];
+            for (int swi = 0; swi < P.sweeps_per_beta; ++swi) {
+                ++done;
+                const bool more = done < total_sweeps;
+                if (push) {
+                    rp_pass<2, GROUPS>(c, beta, more);
+                } else {
+                    const unsigned wacc = rp_pass<0, GROUPS>(c, beta, more);
+                    if (more) {  // CTA-uniform hand-over decision
+                        if (lane == 0) atomicAdd(acc_sh + acc_par, wacc);
+                        __syncthreads();
+                        const unsigned long long tot = acc_sh[acc_par];
+                        if (threadIdx.x == 0) acc_sh[acc_par ^ 1] = 0u;
+                        acc_par ^= 1;
+                        if (tot * 1000ull < (unsigned long long)P.switch_permille * (unsigned long long)n * (unsigned long long)cta_reads) {
+                            rp_pass<1, false>(c, beta, true);
+                            push = true;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- final spins: packed transposed layout for the energy kernel, +-1 bytes for the caller
+        if (active) {
+            for (int wi = 0; wi < nch; ++wi) {
+                const uint32_t w = __ldcg(c.SF + (int64_t)wi * 32).x;
+                D.packedT[(int64_t)wi * D.rpad + r] = w;
+                int8_t *row = D.states + r * (int64_t)n + wi * 32;
+                const int lim = min(32, n - wi * 32);
+                for (int i = 0; i < lim; ++i) row[i] = ((w >> i) & 1u) ? 1 : -1;
+            }
+        }
+    }
+    // warp-reduce the per-lane counters
+    unsigned long long v[5] = {c.st.cand, c.st.draws, c.st.acc, c.st.ties, c.st.nbr};
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL_MASK, v[q], off);
+    if (lane == 0) {
+        atomicAdd(P.stats + ST_CAND, v[0]);
+        atomicAdd(P.stats + ST_DRAWS, v[1]);
+        atomicAdd(P.stats + ST_ACC, v[2]);
+        atomicAdd(P.stats + ST_TIES, v[3]);
+        atomicAdd(P.stats + ST_NBR, v[4]);
+    }
+}

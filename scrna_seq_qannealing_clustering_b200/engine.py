@@ -55,8 +55,13 @@ class Context:
         self.close()
 
     def set_kernel(self, kernel: int):
-        """Reference-mode kernel: _lib.QA_KERNEL_AUTO / QA_KERNEL_WARP_PER_READ / QA_KERNEL_LOCKSTEP_PUSH."""
+        """Reference-mode kernel: _lib.QA_KERNEL_AUTO / QA_KERNEL_WARP_PER_READ / QA_KERNEL_LOCKSTEP_PUSH / QA_KERNEL_REPLAY."""
         check(_lib.load().qa_ctx_set_kernel(self._h, int(kernel)))
+
+    @property
+    def last_kernel(self) -> int:
+        """QA_KERNEL_* the last sampling call actually ran on (after automatic selection / fall-back)."""
+        return check(_lib.load().qa_ctx_last_kernel(self._h))
 
     @property
     def resident_reads(self) -> int:

@@ -14,12 +14,17 @@ from scrna_seq_qannealing_clustering_b200.engine import IsingModel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["warp_per_read", "lockstep_push"])
+KERNELS = {"warp_per_read": _lib.QA_KERNEL_WARP_PER_READ, "lockstep_push": _lib.QA_KERNEL_LOCKSTEP_PUSH,
+           "replay": _lib.QA_KERNEL_REPLAY}
+
+
+@pytest.fixture(params=list(KERNELS))
 def gpu_ctx(request, built):
-    """Every reference-mode test runs on both bit-exact kernels."""
+    """Every reference-mode test runs on all three bit-exact kernels (replay falls back to lockstep_push on dense models)."""
     from scrna_seq_qannealing_clustering_b200.engine import Context
     ctx = Context(0)
-    ctx.set_kernel(_lib.QA_KERNEL_WARP_PER_READ if request.param == "warp_per_read" else _lib.QA_KERNEL_LOCKSTEP_PUSH)
+    ctx.set_kernel(KERNELS[request.param])
+    ctx.requested_kernel = request.param
     yield ctx
     ctx.close()
 
