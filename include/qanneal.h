@@ -81,6 +81,7 @@ typedef struct qa_stats {
     double ms_d2h;          /* device->host copies */
     uint32_t anneal_launches;
     uint32_t total_launches; /* kernels of this library launched by the call */
+    double ms_total;        /* the whole call on the device: first copy-in event to last copy-out event */
 } qa_stats;
 
 const char *qa_last_error(void);

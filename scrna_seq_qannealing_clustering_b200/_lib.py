@@ -62,6 +62,7 @@ class QAStats(C.Structure):
         ("ms_d2h", C.c_double),
         ("anneal_launches", C.c_uint32),
         ("total_launches", C.c_uint32),
+        ("ms_total", C.c_double),
     ]
 
     def as_dict(self) -> dict:

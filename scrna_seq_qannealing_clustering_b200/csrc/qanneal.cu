@@ -127,6 +127,7 @@ struct AnnealParams {
 };
 
 enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
+constexpr int QA_NDEBUG = 8;   // development counters behind the read counter (QA_RP_PROFILE builds print them)
 
 constexpr int QA_TPB_MAX = 256;
 // measured on B200 (config 3): lockstep wins from ~3.5 tiles of 32 reads per SM, warp-per-read below that
@@ -1205,6 +1206,8 @@ struct qa_ctx {
     int replay_switch_permille = 20;  // replay -> push hand-over threshold (QA_REPLAY_SWITCH_PERMILLE overrides)
     int replay_warps = 0;             // warps per CTA of the replay kernel (0: automatic; QA_REPLAY_WARPS overrides)
     int last_kernel = 0;              // QA_KERNEL_* the last sampling call ran on
+    unsigned rp_smem_base = 1024;     // shared-window offset of dynamic shared memory (verified by the replay kernel)
+    bool rp_base_checked = false;
     unsigned long long *d_stats = nullptr;  // QA_NSTAT counters + 1 read counter
     int *d_flag = nullptr;
     double *d_best_e = nullptr;
@@ -1504,6 +1507,7 @@ int build_replay_tables(qa_model *M) {
     std::vector<int32_t> stamp, slot_of;
     std::vector<std::pair<int32_t, double>> later, earlier;
     std::vector<RpEntry> E;
+    std::vector<size_t> hdr_pos;
     for (int p = 0; p < M->num_problems; ++p) {
         const int64_t v_off = M->var_off[p];
         const int n = (int)(M->var_off[p + 1] - v_off);
@@ -1511,6 +1515,7 @@ int build_replay_tables(qa_model *M) {
         const int nch = (n + 31) / 32;
         const int nblk = nch * (32 / RP_D);
         blk_base[p] = (int64_t)off.size();
+        hdr_pos.clear();
         stamp.assign(nch, -1);
         slot_of.assign(nch, 0);
         for (int b = 0; b < nblk; ++b) {
@@ -1542,8 +1547,7 @@ int build_replay_tables(qa_model *M) {
                 std::stable_sort(later.begin(), later.end(), by_index);
                 std::stable_sort(earlier.begin(), earlier.end(), by_index);
                 const size_t deg = later.size() + earlier.size();
-                const size_t padded = (deg + 3) & ~(size_t)3;
-                if (start + padded > (size_t)RP_CAP) return QA_OK;
+                if (start + deg > (size_t)RP_CAP) return QA_OK;
                 H.nlater[i] = (uint16_t)later.size();
                 H.deg[i] = (uint16_t)deg;
                 for (int part = 0; part < 2; ++part) {
@@ -1567,23 +1571,24 @@ int build_replay_tables(qa_model *M) {
                         E.push_back(en);
                     }
                 }
-                for (size_t k = deg; k < padded; ++k) {   // never flagged: the all-zero slot
-                    RpEntry en;
-                    en.J2 = 0.0;
-                    en.j = v;
-                    en.B = (uint32_t)(RP_SLOTS - 1) << 8;
-                    E.push_back(en);
-                }
-                H.row[i] = (uint32_t)start | ((uint32_t)(start + padded) << 16);
+                H.row[i] = (uint32_t)start | ((uint32_t)(start + deg) << 16);
             }
             H.nent = (int32_t)E.size();
             H.nbw = nbw;
             if (slabs.size() / 16 > 0xfffffff0ull) return QA_OK;
             off.push_back((uint32_t)(slabs.size() / 16));
+            hdr_pos.push_back(slabs.size());
             const unsigned char *hp = reinterpret_cast<const unsigned char *>(&H);
             slabs.insert(slabs.end(), hp, hp + sizeof(H));
             const unsigned char *ep = reinterpret_cast<const unsigned char *>(E.data());
             slabs.insert(slabs.end(), ep, ep + E.size() * sizeof(RpEntry));
+        }
+        // every slab also carries the word list of the next block (cyclic) for the L2 run-ahead of its {S,F} rows
+        for (size_t b = 0; b < hdr_pos.size(); ++b) {
+            RpHdr *cur = reinterpret_cast<RpHdr *>(slabs.data() + hdr_pos[b]);
+            const RpHdr *nxt = reinterpret_cast<const RpHdr *>(slabs.data() + hdr_pos[(b + 1) % hdr_pos.size()]);
+            cur->nbw_next = nxt->nbw;
+            memcpy(cur->bw_next, nxt->bw, sizeof(cur->bw_next));
         }
     }
     off.push_back((uint32_t)(slabs.size() / 16));
@@ -1670,7 +1675,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
     }
 
     ctx->last_kernel = kernel;
-    QA_CUDA(cudaMemsetAsync(ctx->d_stats, 0, (QA_NSTAT + 1) * sizeof(unsigned long long), ctx->stream));
+    QA_CUDA(cudaMemsetAsync(ctx->d_stats, 0, (QA_NSTAT + 1 + QA_NDEBUG) * sizeof(unsigned long long), ctx->stream));
     QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
 
     AnnealParams A;
@@ -1736,15 +1741,16 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
     } else if (kernel == QA_KERNEL_REPLAY) {
         // replay: one CTA = `nw` consecutive 32-read tiles of one problem, coupling slabs shared through a TMA ring
         const int tpp = (reads_per_problem + 31) / 32;
+        const int mg = std::max(M->ngroups, 1);
         int nw = ctx->replay_warps;
-        if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {
+        if ((nw != 1 && nw != 2 && nw != 4 && nw != 8 && nw != 16) || nw > RP_MAX_WARPS) {
             nw = 1;
-            while (nw < 8 && nw < tpp) nw *= 2;
+            while (nw < RP_MAX_WARPS && nw < tpp) nw *= 2;
+            while (nw > 1 && rp_smem_bytes(nw, mg, ctx->rp_smem_base) > (size_t)(226 * 1024 / RP_MIN_CTAS - 1024)) nw /= 2;   // RP_MIN_CTAS CTAs per SM
         }
         const int64_t gpp = (tpp + nw - 1) / nw;
         const int64_t total_items = (int64_t)P * gpp;
-        const int mg = std::max(M->ngroups, 1);
-        const size_t smem = rp_smem_bytes(nw, mg);
+        size_t smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
         const void *fn = groups ? (const void *)k_anneal_replay<true> : (const void *)k_anneal_replay<false>;
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
@@ -1782,6 +1788,25 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         QA_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(nw * 32), args, smem, ctx->stream));
         QA_CUDA(cudaGetLastError());
         ctx->launches++;
+        {   // the kernel leaves at once if dynamic shared memory does not start where the layout assumed: relaunch with the real base
+            int fl[2] = {0, 0};
+            QA_CUDA(cudaMemcpyAsync(fl, ctx->d_flag, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
+            if (!ctx->rp_base_checked) {   // first launch of this context only (costs a synchronisation)
+                QA_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (fl[0] == QA_ERR_SMEM_BASE) {
+                    ctx->rp_smem_base = (unsigned)fl[1];
+                    smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
+                    QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
+                    QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
+                    QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+                    QA_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(nw * 32), args, smem, ctx->stream));
+                    QA_CUDA(cudaGetLastError());
+                    ctx->launches++;
+                }
+                ctx->rp_base_checked = true;
+            }
+        }
         if (st) st->anneal_launches++;
         done = total_reads;
     } else {
@@ -1847,10 +1872,15 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
     }
     QA_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     int flag = 0;
-    unsigned long long hs[QA_NSTAT + 1];
+    unsigned long long hs[QA_NSTAT + 1 + QA_NDEBUG];
     QA_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     QA_CUDA(cudaMemcpyAsync(hs, ctx->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
     QA_CUDA(cudaStreamSynchronize(ctx->stream));
+#ifdef QA_RP_PROFILE
+    fprintf(stderr, "[qa profile] cycles summed over warps: setup %llu slab-wait %llu stage-wait %llu prologue %llu entries %llu decide %llu pass %llu push-flip %llu\n",
+            hs[QA_NSTAT + 1], hs[QA_NSTAT + 2], hs[QA_NSTAT + 3], hs[QA_NSTAT + 4], hs[QA_NSTAT + 5], hs[QA_NSTAT + 6], hs[QA_NSTAT + 7], hs[QA_NSTAT + 8]);
+#endif
+    if (flag == QA_ERR_SMEM_BASE) return fail(QA_ERR_CUDA, "replay kernel: dynamic shared memory does not start where the layout assumed");
     if (flag != 0) return fail(flag, "initial states must be +1/-1");
     if (st) {
         st->candidates += hs[ST_CAND];
@@ -1940,6 +1970,7 @@ int sample_common(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *s
     QA_CUDA(cudaStreamSynchronize(ctx->stream));
     st.ms_h2d += elapsed(ctx->ev[0], ctx->ev[1]);
     st.ms_d2h += elapsed(ctx->ev[4], ctx->ev[5]);
+    st.ms_total += elapsed(ctx->ev[0], ctx->ev[5]);
     st.total_launches = ctx->launches - launches0;
     if (stats_out) *stats_out = st;
     return (int)std::min<int64_t>(completed / M->num_problems, 0x7fffffff);
@@ -1985,7 +2016,7 @@ int qa_ctx_create(int device_id, qa_ctx **out) {
     if (const char *e = getenv("QA_REPLAY_WARPS")) ctx->replay_warps = atoi(e);
     QA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) QA_CUDA(cudaEventCreate(&ev));
-    QA_CUDA(cudaMalloc((void **)&ctx->d_stats, (QA_NSTAT + 1) * sizeof(unsigned long long)));
+    QA_CUDA(cudaMalloc((void **)&ctx->d_stats, (QA_NSTAT + 1 + QA_NDEBUG) * sizeof(unsigned long long)));
     QA_CUDA(cudaMalloc((void **)&ctx->d_flag, 2 * sizeof(int)));
     QA_CUDA(cudaMalloc((void **)&ctx->d_best_e, sizeof(double)));
     QA_CUDA(cudaMalloc((void **)&ctx->d_best_i, sizeof(long long)));

@@ -23,28 +23,50 @@
 //
 // Coupling slabs: for every block of RP_D variables the host builds one contiguous slab {RpHdr, RpEntry[]} (replay order,
 // 2J premultiplied, slot/bit of the neighbour's spin word).  All warps of a CTA walk the blocks together; slabs are brought
-// into a 3-stage shared-memory ring by one elected thread with cp.async.bulk (TMA 1-D) completing on mbarriers, and
-// released by one mbarrier arrive per warp -- no __syncthreads in the sweep.
+// into a 4-stage shared-memory ring with cp.async.bulk (TMA 1-D) completing on mbarriers, and released by one mbarrier arrive
+// per warp -- no __syncthreads in the sweep.  There is no fixed producer: whichever warp first gets within RP_DIST blocks of a
+// slab that has not been requested yet claims it (one shared-memory CAS) and issues the copy, so the ring runs at the pace
+// of the fastest warp and nobody waits for a particular (possibly de-prioritised) warp.
 #pragma once
 
-constexpr int RP_D = 16;         // variables per block
-constexpr int RP_CAP = 448;      // entries per slab (rows padded to multiples of 4)
-constexpr int RP_SLOTS = 32;     // spin-word slots per warp: slot 0 = the block's own word, slot 31 = all-zero (padding entries)
-constexpr int RP_MAXBW = 30;     // foreign spin words per block
-constexpr int RP_STAGES = 3;
-constexpr int RP_WARP_BYTES = RP_SLOTS * 32 * 8;  // 8 KB per warp: {~S,F}[slot][lane]; the push phase stages fields here
+#ifndef RP_D
+#define RP_D 16       // variables per block (8 or 16)
+#endif
+constexpr int RP_SLOTS = 2 * RP_D;            // spin-word slots per warp: slot 0 = the block's own word
+constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign spin words per block
+constexpr int RP_CAP = 28 * RP_D;             // entries per slab
+constexpr int RP_STAGES = 4;      // power of two: stage = g & 3, phase = (g >> 2) & 1 for the running block counter g
+#ifndef RP_LA
+#define RP_LA 2     // local fields are loaded this many variables ahead of their visit
+#endif
+#ifndef RP_PF_DIST
+#define RP_PF_DIST (32 / RP_D)   // L2 run-ahead of the field rows, in blocks
+#endif
+constexpr int RP_DIST = 2;        // slabs are requested this many blocks ahead of the first warp that will need them
+constexpr int RP_WARP_BYTES = RP_SLOTS * 32 * 8;  // per warp: {~S,F}[slot][lane]; the push phase stages its fields here
+constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 8;
+#ifndef RP_MAX_WARPS
+#define RP_MAX_WARPS 8    // warps per CTA (upper bound; the host picks a power of two)
+#endif
+#ifndef RP_MIN_CTAS
+#define RP_MIN_CTAS 2     // resident CTAs per SM the register allocation is bounded for
+#endif
 
-struct RpHdr {
-    int32_t nent;            // entries in this slab (with padding)
-    int32_t nbw;             // distinct neighbour words other than the block's own word
-    uint32_t row[16];        // entry range of variable i: start | (padded end << 16)
-    uint16_t nlater[16];     // leading entries of row i that refer to later variables (u > v)
-    uint16_t deg[16];        // true degree of row i (entries [start, start + deg) are real, the rest padding)
-    int32_t ga[16];          // group (low byte, 255: none) | coefficient << 8
-    int32_t bw[RP_MAXBW];    // neighbour word indices, slot s+1 holds word bw[s]
+struct alignas(16) RpHdr {
+    int32_t nent;               // entries in this slab
+    int32_t nbw;                // distinct neighbour words other than the block's own word
+    uint32_t row[RP_D];         // entry range of variable i: start | (end << 16)
+    uint16_t nlater[RP_D];      // leading entries of row i that refer to later variables (u > v)
+    uint16_t deg[RP_D];
+    int32_t ga[RP_D];           // group (low byte, 255: none) | coefficient << 8
+    int32_t bw[RP_MAXBW];       // neighbour word indices, slot s+1 holds word bw[s]
+    int32_t nbw_next;           // the same list for the NEXT block (cyclic): L2 run-ahead of its {S,F} rows
+    int32_t bw_next[RP_MAXBW];
 };
-static_assert(sizeof(RpHdr) == 320, "slab header layout");
-constexpr uint32_t RP_H_NBW = 4, RP_H_ROW = 8, RP_H_NLATER = 72, RP_H_DEG = 104, RP_H_GA = 136, RP_H_BW = 200;
+static_assert(sizeof(RpHdr) % 16 == 0, "slab header layout");
+constexpr uint32_t RP_H_NBW = offsetof(RpHdr, nbw), RP_H_ROW = offsetof(RpHdr, row), RP_H_NLATER = offsetof(RpHdr, nlater),
+                   RP_H_DEG = offsetof(RpHdr, deg), RP_H_GA = offsetof(RpHdr, ga), RP_H_BW = offsetof(RpHdr, bw),
+                   RP_H_NBWN = offsetof(RpHdr, nbw_next), RP_H_BWN = offsetof(RpHdr, bw_next);
 struct __align__(16) RpEntry {
     double J2;     // 2 * J (padding entries: 0)
     int32_t j;     // neighbour (local variable index)
@@ -116,9 +138,10 @@ __device__ __forceinline__ void add_f64_if_neg(double &f, double d, uint32_t t) 
 struct RpCtx {
     // ring (CTA-shared)
     uint32_t full_s, empty_s, stage_s;   // shared addresses: full[0], empty[0] (8 B apart), stage 0
+    unsigned *issued;                    // shared: running index of the next slab to request
     const unsigned char *slabs;          // global slab storage
     const uint32_t *off;                 // [nblk + 1] slab offsets of this problem, in 16-byte units
-    uint32_t stage, phase;               // stage / phase of the next block to consume
+    uint32_t gb;                         // running index of the next block this warp consumes
     // per lane
     double *fT;                          // f[v][lane], this lane's column
     uint2 *SF;                           // {S,F}[word][lane], this lane's column
@@ -131,25 +154,38 @@ struct RpCtx {
     LaneStats st;
     bool active;
     int n, nblk;
+#ifdef QA_RP_PROFILE
+    unsigned long long t_full, t_empty;  // cycles spent waiting for a slab / for a free stage
+    unsigned long long t_setup, t_prol, t_ent, t_dec, t_pass, t_flip;
+#endif
 };
 
-// thread 0 only: start the copy of block `blk` into the stage that follows the one being consumed
-__device__ __forceinline__ void rp_issue_next(const RpCtx &c, int blk) {
-    uint32_t st = c.stage + 1, ph = c.phase;
-    if (st == RP_STAGES) { st = 0; ph ^= 1u; }
-    mbar_wait(c.empty_s + 8u * st, ph ^ 1u);     // every warp has released the previous use of that stage
-    const uint32_t o0 = __ldg(c.off + blk), o1 = __ldg(c.off + blk + 1);
-    const uint32_t bytes = (o1 - o0) * 16u;
-    mbar_expect_tx(c.full_s + 8u * st, bytes);
-    tma_load_1d(c.stage_s + st * (uint32_t)RP_STAGE_BYTES, c.slabs + (size_t)o0 * 16u, bytes, c.full_s + 8u * st);
-}
-// thread 0 only: the first block of a work item goes into the stage about to be consumed
-__device__ __forceinline__ void rp_issue_first(const RpCtx &c) {
-    mbar_wait(c.empty_s + 8u * c.stage, c.phase ^ 1u);
-    const uint32_t o0 = __ldg(c.off), o1 = __ldg(c.off + 1);
-    const uint32_t bytes = (o1 - o0) * 16u;
-    mbar_expect_tx(c.full_s + 8u * c.stage, bytes);
-    tma_load_1d(c.stage_s + c.stage * (uint32_t)RP_STAGE_BYTES, c.slabs + (size_t)o0 * 16u, bytes, c.full_s + 8u * c.stage);
+// lane 0 of any warp: request every slab up to running index `tgt` that nobody has requested yet.  `blk` is the block the
+// calling warp is about to consume (running index c.gb); slabs follow the cyclic block order of the passes.
+__device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
+    unsigned cur = *reinterpret_cast<volatile unsigned *>(c.issued);
+    while ((int)(tgt - cur) >= 0) {
+        const unsigned old = atomicCAS(c.issued, cur, cur + 1u);
+        if (old == cur) {
+            int b = blk + (int)(cur - c.gb);
+            if (b >= c.nblk) b -= c.nblk;
+            const uint32_t st = cur & (RP_STAGES - 1), ph = (cur / RP_STAGES) & 1u;
+#ifdef QA_RP_PROFILE
+            const long long t0 = clock64();
+#endif
+            mbar_wait(c.empty_s + 8u * st, ph ^ 1u);     // every warp has released the previous use of that stage
+#ifdef QA_RP_PROFILE
+            c.t_empty += (unsigned long long)(clock64() - t0);
+#endif
+            const uint32_t o0 = __ldg(c.off + b), o1 = __ldg(c.off + b + 1);
+            const uint32_t bytes = (o1 - o0) * 16u;
+            mbar_expect_tx(c.full_s + 8u * st, bytes);
+            tma_load_1d(c.stage_s + st * (uint32_t)RP_STAGE_BYTES, c.slabs + (size_t)o0 * 16u, bytes, c.full_s + 8u * st);
+            cur = cur + 1u;
+        } else {
+            cur = old;
+        }
+    }
 }
 
 // One pass over all blocks.  MODE 0: replay sweep (pull).  MODE 1: catch-up (pending later-neighbour updates only, no
@@ -166,14 +202,26 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
     unsigned sweep_acc = 0;
     uint32_t S = 0xffffffffu, F = 0u, S0 = 0xffffffffu, F0 = 0u;
 
+#ifdef QA_RP_PROFILE
+    const long long tp0 = clock64();
+#endif
+    const uint32_t g_last = c.gb + (uint32_t)nblk - 1u;   // running index of the last block of this pass
     for (int blk = 0; blk < nblk; ++blk) {
-        if (threadIdx.x == 0) {
-            const bool last = blk == nblk - 1;
-            if (!last || has_next_pass) rp_issue_next(c, last ? 0 : blk + 1);
+        const uint32_t stage = c.gb & (RP_STAGES - 1), phase = (c.gb / RP_STAGES) & 1u;
+        if (lane == 0) {
+            uint32_t tgt = c.gb + (uint32_t)RP_DIST;
+            if (!has_next_pass && (int)(tgt - g_last) > 0) tgt = g_last;
+            rp_request(c, tgt, blk);
         }
         __syncwarp();
-        mbar_wait(c.full_s + 8u * c.stage, c.phase);
-        const uint32_t hdr = c.stage_s + c.stage * (uint32_t)RP_STAGE_BYTES;   // shared address of the slab
+#ifdef QA_RP_PROFILE
+        const long long tw0 = clock64();
+#endif
+        mbar_wait(c.full_s + 8u * stage, phase);
+#ifdef QA_RP_PROFILE
+        if (lane == 0) c.t_full += (unsigned long long)(clock64() - tw0);
+#endif
+        const uint32_t hdr = c.stage_s + stage * (uint32_t)RP_STAGE_BYTES;   // shared address of the slab
         const uint32_t ent = hdr + (uint32_t)sizeof(RpHdr);
         const int v0 = blk * RP_D;
         const int wi = v0 >> 5;
@@ -183,12 +231,24 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
             const uint2 own = __ldcg(SF + (int64_t)wi * 32);
             S = own.x; F = own.y; S0 = S; F0 = F;
         }
-        {   // run-ahead of the field rows two blocks on (L2 prefetch, 128 B per lane = 16 rows)
-            int pv = v0 + 2 * RP_D;
+#ifndef RP_NO_PREFETCH
+        {   // L2 run-ahead of the field rows RP_PF_DIST blocks on: 16 rows x 256 B = 128 sectors, one sector per lane and instruction
+            int pv = v0 + RP_PF_DIST * RP_D;
             if (pv >= nblk * RP_D) pv -= nblk * RP_D;
-            const char *pa = reinterpret_cast<const char *>(fT - lane + (int64_t)pv * 32) + lane * 128;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            const char *pa = reinterpret_cast<const char *>(fT - lane + (int64_t)pv * 32) + lane * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + k * 1024));
         }
+        if (MODE <= 1) {   // ... and of the {S,F} rows the next block will stage (8 sectors per word)
+            const int ns = (int)lds_u32(hdr + RP_H_NBWN) * 8;
+            const char *sfrow = reinterpret_cast<const char *>(SF - lane);
+            for (int k = lane; k < ns; k += 32) {
+                const int64_t w = (int64_t)lds_u32(hdr + RP_H_BWN + 4u * (uint32_t)(k >> 3));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + w * 256 + (k & 7) * 32));
+            }
+            if (sub != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + (int64_t)(wi + 1 < nblk / 2 ? wi + 1 : 0) * 256 + (lane & 7) * 32));
+        }
+#endif
         bool blk_dirty = false;
         if (MODE <= 1) {
             // this lane's copy of every spin/flag word the block refers to (~S so that a set top bit means "spin down")
@@ -210,9 +270,17 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 #pragma unroll
             for (int i = 0; i < RP_D; ++i) sts_f64(sfb + (uint32_t)i * 256u, t[i]);
         }
-        double f_next = 0.0;
-        if (MODE <= 1) f_next = __ldcg(fB);
+        double fq[RP_LA];   // fields of the next RP_LA variables, loaded ahead of their visit
+#pragma unroll
+        for (int k = 0; k < RP_LA; ++k) fq[k] = 0.0;
+        if (MODE <= 1) {
+#pragma unroll
+            for (int k = 0; k < RP_LA; ++k) fq[k] = __ldcg(fB + k * 32);
+        }
         const int ilim = min(RP_D, n - v0);   // uniform: padding variables are not visited
+#ifdef QA_RP_PROFILE
+        c.t_prol += (unsigned long long)(clock64() - tw0) ;
+#endif
 
         for (int i = 0; i < ilim; ++i) {
             const uint32_t rw = lds_u32(hdr + RP_H_ROW + 4u * (uint32_t)i);
@@ -221,41 +289,54 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
             const bool up = (S & bit) != 0u;
             double fv;
             if (MODE <= 1) {
-                fv = f_next;
-                if (i + 1 < RP_D) f_next = __ldcg(fB + (i + 1) * 32);
+                fv = fq[0];
+#pragma unroll
+                for (int k = 0; k + 1 < RP_LA; ++k) fq[k] = fq[k + 1];
+                if (i + RP_LA < RP_D) fq[RP_LA - 1] = __ldcg(fB + (i + RP_LA) * 32);
                 const double f0 = fv;
-                if (MODE == 0) {
-                    // four entries per round: table entries first, then the lane's {~S,F} words, then the ordered additions
-                    // (rows are padded to a multiple of four with entries that point at the all-zero slot: never flagged)
-                    const uint32_t a1 = ent + (rw >> 16) * 16u;
-                    for (uint32_t a = a0; a < a1; a += 64u) {
-                        int4 q[4];
-                        uint2 sf[4];
+#ifdef QA_RP_PROFILE
+                const long long te0 = clock64();
+#endif
+                // a neighbour that did not flip contributes -0.0, the exact additive identity: the only serial dependence of
+                // a replay is one DADD per entry
+                auto replay1 = [&](const int4 &q, const uint2 &sf) {
+                    const uint32_t B = (uint32_t)q.w;
+                    const uint32_t sg = __funnelshift_l(0u, sf.x, B) & 0x80000000u;   // spin down: add -2J
+                    const bool flagged = (int)__funnelshift_l(0u, sf.y, B) < 0;
+                    const int hi = flagged ? (q.y ^ (int)sg) : (int)0x80000000u;
+                    const int lo = flagged ? q.x : 0;
+                    fv += __hiloint2double(hi, lo);
+                };
+                const uint32_t a1 = (MODE == 0) ? ent + (rw >> 16) * 16u
+                                                : a0 + lds_u16(hdr + RP_H_NLATER + 2u * (uint32_t)i) * 16u;
+                uint32_t a = a0;
+                // four entries per round: table entries first, then the lane's {~S,F} words, then the ordered additions
+                for (; a + 64u <= a1; a += 64u) {
+                    int4 q[4];
+                    uint2 sf[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) q[k] = lds_v4(a + 16u * k);
+                    for (int k = 0; k < 4; ++k) q[k] = lds_v4(a + 16u * k);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) sf[k] = lds_u2(((uint32_t)q[k].w & 0x1F00u) | sfb);
+                    for (int k = 0; k < 4; ++k) sf[k] = lds_u2(((uint32_t)q[k].w & RP_SLOT_MASK) | sfb);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t B = (uint32_t)q[k].w;
-                            const uint32_t sg = __funnelshift_l(0u, sf[k].x, B) & 0x80000000u;   // spin down: add -2J
-                            add_f64_if_neg(fv, __hiloint2double(q[k].y ^ (int)sg, q[k].x), __funnelshift_l(0u, sf[k].y, B));
-                        }
-                    }
-                } else {
-                    const uint32_t a1 = a0 + lds_u16(hdr + RP_H_NLATER + 2u * (uint32_t)i) * 16u;
-                    for (uint32_t a = a0; a < a1; a += 16u) {
-                        const int4 q = lds_v4(a);
-                        const uint2 sf = lds_u2(((uint32_t)q.w & 0x1F00u) | sfb);
-                        const uint32_t sg = __funnelshift_l(0u, sf.x, (uint32_t)q.w) & 0x80000000u;
-                        add_f64_if_neg(fv, __hiloint2double(q.y ^ (int)sg, q.x), __funnelshift_l(0u, sf.y, (uint32_t)q.w));
-                    }
+                    for (int k = 0; k < 4; ++k) replay1(q[k], sf[k]);
+                }
+                for (; a < a1; a += 16u) {
+                    const int4 q = lds_v4(a);
+                    const uint2 sf = lds_u2(((uint32_t)q.w & RP_SLOT_MASK) | sfb);
+                    replay1(q, sf);
                 }
                 if (fv != f0) __stcg(fB + i * 32, fv);
+#ifdef QA_RP_PROFILE
+                c.t_ent += (unsigned long long)(clock64() - te0);
+#endif
                 if (MODE == 1) continue;
             } else {
                 fv = lds_f64(sfb + (uint32_t)i * 256u);
             }
+#ifdef QA_RP_PROFILE
+            const long long td0 = clock64();
+#endif
             double dE = up ? -2.0 * fv : 2.0 * fv;
             int g = 255, a = 0;
             if (GROUPS) {
@@ -273,6 +354,9 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                 if (cand) c.st.cand++;
                 acc = ls_accept(dE, cand, beta, c.s0, c.s1, c.st);
             }
+#ifdef QA_RP_PROFILE
+            c.t_dec += (unsigned long long)(clock64() - td0);
+#endif
             if (MODE == 0) {
                 // F[v] := accepted (also when nothing was accepted: the flag of the previous visit must be cleared)
                 F = acc ? (F | bit) : (F & ~bit);
@@ -290,6 +374,9 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                 const unsigned accm = __ballot_sync(FULL_MASK, acc);
                 if (accm == 0u) continue;
                 sweep_acc += __popc(accm);
+#ifdef QA_RP_PROFILE
+                const long long tf0 = clock64();
+#endif
                 const int sgn = up ? (int)0x80000000u : 0;   // f[j] += -2 s_v J
                 const uint32_t deg = lds_u16(hdr + RP_H_DEG + 2u * (uint32_t)i);
                 const uint32_t a1 = a0 + deg * 16u;
@@ -305,6 +392,9 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                         red_add_f64_if(fT + (int64_t)q.z * 32, d, acc);
                     }
                 }
+#ifdef QA_RP_PROFILE
+                c.t_flip += (unsigned long long)(clock64() - tf0);
+#endif
                 if (acc) {
                     S ^= bit;
                     c.st.acc++;
@@ -326,9 +416,12 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
         }
         // release the stage: one arrive per warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(c.empty_s + 8u * c.stage);
-        if (++c.stage == RP_STAGES) { c.stage = 0; c.phase ^= 1u; }
+        if (lane == 0) mbar_arrive(c.empty_s + 8u * stage);
+        ++c.gb;
     }
+#ifdef QA_RP_PROFILE
+    c.t_pass += (unsigned long long)(clock64() - tp0);
+#endif
     return sweep_acc;
 }
 
@@ -354,39 +447,57 @@ __device__ __forceinline__ double rp_field_direct(const ProblemDesc &D, const ui
     return fv;
 }
 
-__host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups) {
-    size_t b = 8192;                                    // slack to align the warp regions to 8 KB
-    b += (size_t)nw * RP_WARP_BYTES;
-    b += (size_t)RP_STAGES * RP_STAGE_BYTES;
-    b += 8 * (2 * RP_STAGES) + 32;                      // mbarriers + CTA scratch
+// Shared-memory layout: [slab stages][mbarriers][CTA scratch][lambda][kappa][group counters] then, aligned to its size in the
+// shared window (so that a slot address is formed by OR), one RP_WARP_BYTES region per warp.  `smem_base` is the shared-window
+// offset of the dynamic allocation (1 KB on sm_100: the system-reserved bytes); the kernel verifies the assumption.
+__host__ __device__ inline size_t rp_fixed_bytes(int nw, int max_groups) {
+    size_t b = (size_t)RP_STAGES * RP_STAGE_BYTES + 8 * (2 * RP_STAGES) + 32;
     b += (sizeof(double) + sizeof(long long)) * (size_t)max_groups;
     b += sizeof(int) * (size_t)max_groups * nw * 32;
     return b;
 }
+__host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned smem_base) {
+    const size_t fixed = rp_fixed_bytes(nw, max_groups);
+    const size_t pad = (RP_WARP_BYTES - (smem_base + fixed) % RP_WARP_BYTES) % RP_WARP_BYTES;
+    return fixed + pad + (size_t)nw * RP_WARP_BYTES;
+}
+constexpr int QA_ERR_SMEM_BASE = -100;   // internal: the dynamic shared memory does not start where the host assumed
 
 template <bool GROUPS>
-__global__ void __launch_bounds__(256, 2) k_anneal_replay(AnnealParams P) {
+__global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_replay(AnnealParams P) {
     extern __shared__ __align__(16) unsigned char rp_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int NW = blockDim.x >> 5;
     const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(rp_raw);
-    const uint32_t base_s = (raw_s + 8191u) & ~8191u;
-    unsigned char *base = rp_raw + (base_s - raw_s);
-    unsigned char *stages = base + (size_t)NW * RP_WARP_BYTES;
-    unsigned char *tail = stages + (size_t)RP_STAGES * RP_STAGE_BYTES;
-    const uint32_t bars_s = base_s + (uint32_t)NW * RP_WARP_BYTES + (uint32_t)RP_STAGES * RP_STAGE_BYTES;
-    long long *item_sh = reinterpret_cast<long long *>(tail + 8 * (2 * RP_STAGES));
-    unsigned *acc_sh = reinterpret_cast<unsigned *>(tail + 8 * (2 * RP_STAGES) + 8);   // [2]
+    const uint32_t fixed = (uint32_t)rp_fixed_bytes(NW, P.max_groups);
+    const uint32_t base_s = (raw_s + fixed + (uint32_t)RP_WARP_BYTES - 1u) & ~((uint32_t)RP_WARP_BYTES - 1u);    // warp regions
+    {
+        uint32_t dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (base_s - raw_s + (uint32_t)NW * RP_WARP_BYTES > dyn) {   // uniform: report the real base and leave
+            if (threadIdx.x == 0) {
+                P.error_flag[1] = (int)raw_s;
+                atomicExch(P.error_flag, QA_ERR_SMEM_BASE);
+            }
+            return;
+        }
+    }
+    unsigned char *tail = rp_raw + (size_t)RP_STAGES * RP_STAGE_BYTES;
+    const uint32_t bars_s = raw_s + (uint32_t)RP_STAGES * RP_STAGE_BYTES;
+    unsigned *issued_sh = reinterpret_cast<unsigned *>(tail + 8 * (2 * RP_STAGES));
+    long long *item_sh = reinterpret_cast<long long *>(tail + 8 * (2 * RP_STAGES) + 8);
+    unsigned *acc_sh = reinterpret_cast<unsigned *>(tail + 8 * (2 * RP_STAGES) + 16);   // [2]
     double *lam_sh = reinterpret_cast<double *>(tail + 8 * (2 * RP_STAGES) + 32);
     long long *kap_sh = reinterpret_cast<long long *>(lam_sh + P.max_groups);
     int *M_all = reinterpret_cast<int *>(kap_sh + P.max_groups);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RP_STAGES; ++s) {
-            mbar_init(bars_s + 8u * s, 1);                     // full: the producer's arrive.expect_tx
+            mbar_init(bars_s + 8u * s, 1);                     // full: the requester's arrive.expect_tx
             mbar_init(bars_s + 8u * (RP_STAGES + s), NW);      // empty: one arrive per warp
         }
+        *issued_sh = 0u;
         acc_sh[0] = 0u;
         acc_sh[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -403,11 +514,15 @@ __global__ void __launch_bounds__(256, 2) k_anneal_replay(AnnealParams P) {
     RpCtx c;
     c.full_s = bars_s;
     c.empty_s = bars_s + 8u * RP_STAGES;
-    c.stage_s = base_s + (uint32_t)NW * RP_WARP_BYTES;
-    c.stage = 0;
-    c.phase = 0;
+    c.stage_s = raw_s;
+    c.issued = issued_sh;
+    c.gb = 0u;
+#ifdef QA_RP_PROFILE
+    c.t_full = 0ull;
+    c.t_empty = 0ull;
+    c.t_setup = c.t_prol = c.t_ent = c.t_dec = c.t_pass = c.t_flip = 0ull;
+#endif
     c.sfbase_s = base_s + (uint32_t)wib * RP_WARP_BYTES + (uint32_t)lane * 8u;
-    sts_u2(c.sfbase_s + (uint32_t)(RP_SLOTS - 1) * 256u, 0u, 0u);   // the all-zero slot of the padding entries
     c.Mcol = M_all + threadIdx.x;
     c.mstride = (int)blockDim.x;
     c.lam = lam_sh;
@@ -437,8 +552,11 @@ __global__ void __launch_bounds__(256, 2) k_anneal_replay(AnnealParams P) {
         c.slabs = D.rp_slabs;
         c.off = D.rp_off;
         const long long total_sweeps = (long long)P.num_betas * P.sweeps_per_beta;
-        if (threadIdx.x == 0 && total_sweeps > 0) rp_issue_first(c);   // overlaps with the set-up below
+        if (lane == 0 && total_sweeps > 0) rp_request(c, c.gb + (uint32_t)RP_DIST, 0);   // overlaps with the set-up below
 
+#ifdef QA_RP_PROFILE
+        const long long ts0 = clock64();
+#endif
         const unsigned long long sd = active ? P.seeds[D.read_base + r] : 1ull;
         c.s0 = sd ? sd : ~0ull;
         c.s1 = 0;
@@ -480,6 +598,9 @@ __global__ void __launch_bounds__(256, 2) k_anneal_replay(AnnealParams P) {
                 e0 = e1;
             }
         }
+#ifdef QA_RP_PROFILE
+        c.t_setup += (unsigned long long)(clock64() - ts0);
+#endif
         // ---- the schedule: replay sweeps while flips are frequent, then one catch-up pass and push sweeps
         bool push = false;
         long long done = 0;
@@ -522,6 +643,19 @@ __global__ void __launch_bounds__(256, 2) k_anneal_replay(AnnealParams P) {
 #pragma unroll
     for (int q = 0; q < 5; ++q)
         for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL_MASK, v[q], off);
+#ifdef QA_RP_PROFILE
+    if (lane == 0) {   // development build: cycles spent waiting on the ring, reported through the otherwise unused counters
+        unsigned long long *dbg = P.stats + QA_NSTAT + 1;
+        atomicAdd(dbg + 0, c.t_setup);
+        atomicAdd(dbg + 1, c.t_full);
+        atomicAdd(dbg + 2, c.t_empty);
+        atomicAdd(dbg + 3, c.t_prol);
+        atomicAdd(dbg + 4, c.t_ent);
+        atomicAdd(dbg + 5, c.t_dec);
+        atomicAdd(dbg + 6, c.t_pass);
+        atomicAdd(dbg + 7, c.t_flip);
+    }
+#endif
     if (lane == 0) {
         atomicAdd(P.stats + ST_CAND, v[0]);
         atomicAdd(P.stats + ST_DRAWS, v[1]);
