@@ -458,17 +458,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// accept test of one variable for every lane (read) of the warp; returns the per-lane accept flag
+// accept test of one variable for every lane (read) of the warp; returns the per-lane accept flag.
+// neal: flip iff exp(-dE*beta) * 2^64 > (double)rand.  Evaluating the fp64 exp for every draw is the longest dependent chain
+// of a step, so the draw is first screened against a single-precision estimate: pa = ex2.approx(float(x) * log2 e) is
+// within 1e-5 relative of exp(x) for x in [-44.4, 0] (conversion 9e-8 of x <= 44, i.e. 4e-6 in the exponent, plus 2 ulp
+// of ex2.approx), so a draw outside [pa * (1 - 1e-4), pa * (1 + 1e-4)] * 2^64 is decided exactly as the fp64 comparison
+// would decide it.  Only draws inside that band (2e-4 of them) take the fp64 path -- the result is identical by construction,
+// and near ties (|p - r| <= 2^-48 p) can only occur inside the band, where they are still counted.
 __device__ __forceinline__ bool ls_accept(double dE, bool cand, double beta, unsigned long long &s0, unsigned long long &s1,
                                           LaneStats &st) {
     bool acc = cand;
-    if (cand && dE > 0.0) {
+    const bool need = cand && dE > 0.0;
+    bool exact = false;
+    double x = 0.0, rd = 0.0;
+    if (need) {
         const unsigned long long rnd = rng_next(s0, s1);
         st.draws++;
-        const double p = exp(-dE * beta) * QA_TWO64;
-        const double rd = __ull2double_rn(rnd);
-        acc = p > rd;
-        if (fabs(p - rd) <= p * 3.5527136788005009e-15) st.ties++;
+        x = -dE * beta;
+        rd = __ull2double_rn(rnd);
+        float pa;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pa) : "f"(__double2float_rn(x) * 1.44269504088896341f));
+        const double pd = (double)pa * QA_TWO64;
+        acc = rd < pd * 0.9999;
+        exact = !acc && !(rd > pd * 1.0001);
+    }
+    if (__any_sync(FULL_MASK, exact)) {
+        if (exact) {
+            const double p = exp(x) * QA_TWO64;
+            acc = p > rd;
+            if (fabs(p - rd) <= p * 3.5527136788005009e-15) st.ties++;
+        }
     }
     return acc;
 }
@@ -1243,6 +1262,7 @@ struct qa_model {
     unsigned char *rp_slabs = nullptr;
     uint32_t *rp_off = nullptr;
     bool rp_built = false, rp_ok = false;
+    bool groups_i32 = false;   // every group term a*(a - s*(M+kappa)) fits 32-bit integers
 };
 
 namespace {
@@ -1751,7 +1771,8 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         const int64_t gpp = (tpp + nw - 1) / nw;
         const int64_t total_items = (int64_t)P * gpp;
         size_t smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
-        const void *fn = groups ? (const void *)k_anneal_replay<true> : (const void *)k_anneal_replay<false>;
+        const void *fn = !groups ? (const void *)k_anneal_replay<0>
+                                 : (M->groups_i32 ? (const void *)k_anneal_replay<1> : (const void *)k_anneal_replay<2>);
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
         QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, nw * 32, smem, cudaOccupancyDefault));
@@ -2120,10 +2141,12 @@ int qa_model_set_groups(qa_model *M, int32_t ngroups, const int32_t *grp, const 
             maxa[tg[v]] = std::max(maxa[tg[v]], std::fabs((double)tc[v]));
         }
     }
+    M->groups_i32 = true;
     for (int g = 0; g < ngroups; ++g) {
         const double span = sumabs[g] + std::fabs((double)hk[g]);
         if (span >= 2147483648.0 || maxa[g] * (maxa[g] + span) >= 9007199254740992.0)
             return fail(QA_ERR_LIMIT, "group coefficients too large for exact integer evaluation");
+        if (maxa[g] * (maxa[g] + span) >= 2147483648.0) M->groups_i32 = false;
     }
     QA_CUDA(cudaMalloc((void **)&M->grp, npad * sizeof(int32_t)));
     QA_CUDA(cudaMalloc((void **)&M->coef, npad * sizeof(int32_t)));

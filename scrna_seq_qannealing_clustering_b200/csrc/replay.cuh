@@ -190,7 +190,8 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
 
 // One pass over all blocks.  MODE 0: replay sweep (pull).  MODE 1: catch-up (pending later-neighbour updates only, no
 // decisions).  MODE 2: push sweep (neal's eager form).  Returns the number of accepted flips of the warp.
-template <int MODE, bool GROUPS>
+// GROUPS: 0 none, 1 rank-1 groups with 32-bit exact integer arithmetic (host-checked ranges), 2 with 64-bit
+template <int MODE, int GROUPS>
 __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
     const int lane = threadIdx.x & 31;
     const double thr = 44.36142 / beta;
@@ -344,8 +345,14 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                 g = ga & 255;
                 if (g != 255) {
                     a = ga >> 8;
-                    const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)c.Mcol[g * c.mstride] + c.kap[g]));
-                    dE = dE + c.lam[g] * (double)t;
+                    if (GROUPS == 1) {
+                        const int m = c.Mcol[g * c.mstride] + reinterpret_cast<const int *>(c.kap)[2 * g];
+                        const int t = a * (a - (up ? m : -m));
+                        dE = dE + c.lam[g] * (double)t;
+                    } else {
+                        const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)c.Mcol[g * c.mstride] + c.kap[g]));
+                        dE = dE + c.lam[g] * (double)t;
+                    }
                 }
             }
             const bool cand = active && !(dE >= thr);
@@ -463,7 +470,7 @@ __host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned
 }
 constexpr int QA_ERR_SMEM_BASE = -100;   // internal: the dynamic shared memory does not start where the host assumed
 
-template <bool GROUPS>
+template <int GROUPS>
 __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_replay(AnnealParams P) {
     extern __shared__ __align__(16) unsigned char rp_raw[];
     const int lane = threadIdx.x & 31;
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                         if (threadIdx.x == 0) acc_sh[acc_par ^ 1] = 0u;
                         acc_par ^= 1;
                         if (tot * 1000ull < (unsigned long long)P.switch_permille * (unsigned long long)n * (unsigned long long)cta_reads) {
-                            rp_pass<1, false>(c, beta, true);
+                            rp_pass<1, 0>(c, beta, true);
                             push = true;
                         }
                     }
