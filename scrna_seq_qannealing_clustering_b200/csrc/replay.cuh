@@ -101,12 +101,12 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 // shared-memory accesses by explicit address (volatile: kept in program order among themselves and after the barrier waits)
 __device__ __forceinline__ int4 lds_v4(uint32_t a) {
     int4 r;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
     return r;
 }
 __device__ __forceinline__ uint2 lds_u2(uint32_t a) {
     uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
     return r;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
