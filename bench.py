@@ -322,7 +322,14 @@ def main():
     ms_kernel = stats_acc["ms_anneal"] / launches
     alg = algorithmic_bytes(stats_acc) / launches
     achieved = alg / (ms_kernel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # measured DRAM bytes of the same launch shape, from the committed ncu launch list (a bench value is never taken under ncu)
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic_replay_config3.json"
+    if tfile.exists():
+        t = json.loads(tfile.read_text())
+        if (t["kernel"], t["reads"], t["num_sweeps"], t["num_variables"]) == (kernel_used, R, len(betas) * spb, n):
+            traffic = t["dram_bytes_per_launch"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": KERNEL_NAMES.get(kernel_used, str(kernel_used)), "ms_per_launch": ms_kernel,
                 "algorithmic_bytes_per_launch": alg, "survey_formula_GBps": survey_bytes(stats_acc) / launches / (ms_kernel * 1e-3) / 1e9,
                 "acceptance": stats_acc["accepted"] / stats_acc["attempts"],

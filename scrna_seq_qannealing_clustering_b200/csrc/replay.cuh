@@ -616,6 +616,10 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
             for (int swi = 0; swi < P.sweeps_per_beta; ++swi) {
                 ++done;
                 const bool more = done < total_sweeps;
+#ifdef QA_RP_PROFILE
+                if (blockIdx.x == 0 && threadIdx.x == 0)
+                    printf("[qa sweep] %lld beta %.4g mode %s clock %lld\n", done, beta, push ? "push" : "replay", clock64());
+#endif
                 if (push) {
                     rp_pass<2, GROUPS>(c, beta, more);
                 } else {
