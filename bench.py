@@ -186,10 +186,23 @@ def main_reference(args):
                          "sample": f"{reads} reads x {len(betas) * spb} sweeps x {model.num_variables} vars per step, OpenMP over reads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict):
+    """Rank 0 prints ONE JSON line on the real stdout (libraries such as NCCL may write banners to fd 1: it is pointed at
+    stderr for the duration of the run, see main())."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -355,7 +368,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "best_energy": float(energies_dev.min().item() + model.offset),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     gm.close()
     ctx.close()
     if world > 1:
