@@ -1680,10 +1680,12 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         kernel = QA_KERNEL_LOCKSTEP_PUSH;
     if (kernel == QA_KERNEL_LOCKSTEP_PULL && seed_mode != QA_SEED_PER_READ)
         return fail(QA_ERR_ARG, "throughput mode needs per-read seeding");
-    // replay kernel (deferred exact updates): sparse models whose blocks fit the slab format; explicit choice, or
-    // automatic wherever the lockstep push kernel would have been taken
+    // replay kernel (deferred exact updates): sparse models whose blocks fit the slab format; explicit choice, or automatic
+    // from 6144 reads on (measured on B200, config 3: 1.26e10 vs 7.5e9 attempts/s for the warp-per-read kernel at 12 500
+    // reads, 4.3e9 vs 5.9e9 at 4096)
     if (mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ &&
-        (ctx->kernel == QA_KERNEL_REPLAY || (ctx->kernel == QA_KERNEL_AUTO && kernel == QA_KERNEL_LOCKSTEP_PUSH))) {
+        (ctx->kernel == QA_KERNEL_REPLAY ||
+         (ctx->kernel == QA_KERNEL_AUTO && (int64_t)reads_per_problem >= 32 && total_reads >= 6144))) {
         rc = build_replay_tables(M);
         if (rc) return rc;
         if (M->rp_ok) {
@@ -1767,6 +1769,8 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
             nw = 1;
             while (nw < RP_MAX_WARPS && nw < tpp) nw *= 2;
             while (nw > 1 && rp_smem_bytes(nw, mg, ctx->rp_smem_base) > (size_t)(226 * 1024 / RP_MIN_CTAS - 1024)) nw /= 2;   // RP_MIN_CTAS CTAs per SM
+            // few tiles: prefer narrower CTAs on every SM to full CTAs on some of them
+            while (nw > 1 && (int64_t)P * ((tpp + nw - 1) / nw) < 2 * (int64_t)ctx->num_sms) nw /= 2;
         }
         const int64_t gpp = (tpp + nw - 1) / nw;
         const int64_t total_items = (int64_t)P * gpp;
