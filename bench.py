@@ -139,16 +139,19 @@ def survey_bytes(stats: dict) -> float:
     return 8.0 * stats["attempts"] + 9.0 * stats["accepted"] + 17.0 * stats["nbr_updates"] + 12.0 * stats["nbr_updates"]
 
 
-def run_cpu_sample(model, betas, spb, seed, reads, threads):
+def run_cpu_sample(model, betas, spb, seed, reads, threads, states=None, seeds=None):
+    """The CPU restatement on `reads` reads (its own seeded inputs, or the given initial states / per-read seeds)."""
     from oracle import oracle
     from scrna_seq_qannealing_clustering_b200 import schedule
-    states = schedule.random_spin_states(reads, model.num_variables, seed)
-    seeds = schedule.per_read_seeds(seed, reads)
+    if states is None:
+        states = schedule.random_spin_states(reads, model.num_variables, seed)
+    if seeds is None:
+        seeds = schedule.per_read_seeds(seed, reads)
     t0 = time.perf_counter()
     e, st = oracle.sample_ising(model.h, model.starts, model.ends, model.weights, states, betas, spb, seeds,
                                 groups=model.groups.astuple() if model.groups is not None else None, nthreads=threads)
     dt = time.perf_counter() - t0
-    return st["attempts"] / dt, dt, float(e.min() + model.offset)
+    return st["attempts"] / dt, dt, float(e.min() + model.offset), states
 
 
 def peaks():
@@ -172,7 +175,7 @@ def main_reference(args):
         run_cpu_sample(model, betas[: max(1, len(betas) // 50)], spb, args.seed, threads, threads)
     rates, times = [], []
     for s in range(args.steps):
-        r, dt, _ = run_cpu_sample(model, betas, spb, args.seed + s, reads, threads)
+        r, dt, _, _ = run_cpu_sample(model, betas, spb, args.seed + s, reads, threads)
         rates.append(r)
         times.append(dt)
     total_attempts = model.num_variables * len(betas) * spb * reads * args.steps
@@ -356,9 +359,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
         reads = args.cpu_reads or 8 * threads
-        v, dt, _ = run_cpu_sample(model, betas, spb, args.seed, reads, threads)
+        # the CPU sample anneals the FIRST `reads` reads of the GPU step (same initial states, same per-read seeds), so it is
+        # also a full-size parity check: the GPU's final states of those reads must equal the CPU's byte for byte
+        reads = min(reads, R)
+        cpu_states = init_host[:reads].numpy().copy()
+        v, dt, _, cpu_states = run_cpu_sample(model, betas, spb, args.seed, reads, threads, states=cpu_states, seeds=seeds[:reads])
+        gpu_states = states_dev[:reads].cpu().numpy()
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
-               "sample": f"{reads} reads x {len(betas) * spb} sweeps x {n} vars of the same workload, OpenMP over reads"}
+               "sample": f"{reads} reads x {len(betas) * spb} sweeps x {n} vars of the same workload, OpenMP over reads",
+               "parity_check": {"reads": int(reads), "final_states_identical_to_gpu": bool(np.array_equal(cpu_states, gpu_states))}}
 
     if rank == 0:
         line = {

@@ -90,7 +90,9 @@ struct ProblemDesc {
     const unsigned short *ent_slot; // indexed like col: slot | (bit << 8)
     // coupling slabs of the replay kernel (null until built): one {RpHdr, RpEntry[]} per block of 16 variables
     const unsigned char *rp_slabs;  // global slab storage
-    const uint32_t *rp_off;         // [nblk + 1] slab offsets of this problem in 16-byte units
+    const uint32_t *rp_off;         // [rp_nslabs + 1] slab offsets of this problem in 16-byte units
+    int32_t rp_nslabs;              // blocks (slabs) of this problem
+    int32_t pad2_;
 };
 
 struct AnnealParams {
@@ -1262,6 +1264,7 @@ struct qa_model {
     unsigned char *rp_slabs = nullptr;
     uint32_t *rp_off = nullptr;
     bool rp_built = false, rp_ok = false;
+    bool rp_uniform = false;   // every block holds exactly RP_D variables
     bool groups_i32 = false;   // every group term a*(a - s*(M+kappa)) fits 32-bit integers
 };
 
@@ -1391,7 +1394,7 @@ int finalize_descs(qa_model *M) {
         D.w = M->w + c0;
         D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
         D.bw_ptr = nullptr; D.bw_words = nullptr; D.ent_slot = nullptr;
-        D.rp_slabs = nullptr; D.rp_off = nullptr;
+        D.rp_slabs = nullptr; D.rp_off = nullptr; D.rp_nslabs = 0;
         M->n_max = std::max(M->n_max, D.n);
     }
     M->nch_max = (M->n_max + 31) / 32;
@@ -1496,8 +1499,10 @@ int build_word_tables(qa_model *M) {
 // Coupling slabs of the replay kernel (replay.cuh): per block of RP_D variables one contiguous {RpHdr, RpEntry[]} record
 // with the rows in REPLAY order -- neighbours u > v ascending, then u < v ascending (stable, so duplicate couplers keep their
 // adjacency order) -- 2J premultiplied, and the slot / bit of the neighbour's spin word.  Built once per model on the host
-// from the device-built CSR (a setup step, O(entries)).  Models that do not fit the format (a block with more than RP_CAP
-// entries or more than RP_SLOTS-1 foreign spin words, i.e. dense models) leave rp_ok false and run on the other kernels.
+// from the device-built CSR (a setup step, O(entries)).  Consecutive variables are packed greedily into blocks of at most RP_D
+// variables, RP_CAP entries and RP_MAXBW foreign spin words, never across a 32-variable spin word.  Models whose blocks would
+// hold fewer than 4 variables on average (dense rows, or sparse rows scattered over many words) leave rp_ok false and run on
+// the other kernels.
 int build_replay_tables(qa_model *M) {
     if (M->rp_built) return QA_OK;
     qa_ctx *ctx = M->ctx;
@@ -1528,46 +1533,61 @@ int build_replay_tables(qa_model *M) {
     std::vector<std::pair<int32_t, double>> later, earlier;
     std::vector<RpEntry> E;
     std::vector<size_t> hdr_pos;
+    std::vector<int32_t> nslabs(M->num_problems, 0);
+    bool uniform = true;
+    std::vector<int32_t> row_words;
     for (int p = 0; p < M->num_problems; ++p) {
         const int64_t v_off = M->var_off[p];
         const int n = (int)(M->var_off[p + 1] - v_off);
         if (n == 0) return QA_OK;
         const int nch = (n + 31) / 32;
-        const int nblk = nch * (32 / RP_D);
+        const int npad = nch * 32;
         blk_base[p] = (int64_t)off.size();
         hdr_pos.clear();
         stamp.assign(nch, -1);
         slot_of.assign(nch, 0);
-        for (int b = 0; b < nblk; ++b) {
-            const int v0 = b * RP_D;
+        int b = 0;   // block (slab) index inside the problem; doubles as the stamp of the word -> slot map
+        for (int v0 = 0; v0 < npad; ++b) {
             const int own = v0 >> 5;
+            const int vmax = std::min({v0 + RP_D, (own + 1) * 32});   // never across a spin word
             RpHdr H;
             memset(&H, 0, sizeof(H));
+            for (int i = 0; i < RP_D; ++i) H.ga[i] = 255;
             E.clear();
-            int nbw = 0;
-            for (int i = 0; i < RP_D; ++i) {
-                const int v = v0 + i;
-                const size_t start = E.size();
-                H.row[i] = (uint32_t)start | ((uint32_t)start << 16);
-                H.ga[i] = 255;
-                H.nlater[i] = 0;
-                H.deg[i] = 0;
-                if (v >= n) continue;
-                if (M->ngroups > 0 && hg[v] >= 0) {
-                    if (hc[v] >= (1 << 23) || hc[v] <= -(1 << 23)) return QA_OK;  // coefficient does not fit the packed form
-                    H.ga[i] = (int32_t)((uint32_t)hg[v] | ((uint32_t)hc[v] << 8));
-                }
+            int nbw = 0, nv = 0;
+            for (int v = v0; v < vmax; ++v) {
+                // the row of v in replay order
                 later.clear();
                 earlier.clear();
-                for (int64_t e = rowptr[v_off + v]; e < rowptr[v_off + v + 1]; ++e) {
-                    if (col[e] > v) later.emplace_back(col[e], val[e]);
-                    else earlier.emplace_back(col[e], val[e]);
+                if (v < n) {
+                    for (int64_t e = rowptr[v_off + v]; e < rowptr[v_off + v + 1]; ++e) {
+                        if (col[e] > v) later.emplace_back(col[e], val[e]);
+                        else earlier.emplace_back(col[e], val[e]);
+                    }
                 }
-                auto by_index = [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b) { return a.first < b.first; };
+                auto by_index = [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b2) { return a.first < b2.first; };
                 std::stable_sort(later.begin(), later.end(), by_index);
                 std::stable_sort(earlier.begin(), earlier.end(), by_index);
                 const size_t deg = later.size() + earlier.size();
-                if (start + deg > (size_t)RP_CAP) return QA_OK;
+                // does the row still fit into this block?  (entries, and the foreign spin words it would add)
+                row_words.clear();
+                for (int part = 0; part < 2; ++part)
+                    for (const auto &nb : (part == 0 ? later : earlier)) {
+                        const int wj = nb.first >> 5;
+                        if (wj != own && stamp[wj] != b && std::find(row_words.begin(), row_words.end(), wj) == row_words.end())
+                            row_words.push_back(wj);
+                    }
+                const bool fits = E.size() + deg <= (size_t)RP_CAP && nbw + (int)row_words.size() <= RP_MAXBW;
+                if (!fits) {
+                    if (nv == 0) return QA_OK;   // a single row exceeds the format: dense model
+                    break;
+                }
+                const int i = nv++;
+                const size_t start = E.size();
+                if (v < n && M->ngroups > 0 && hg[v] >= 0) {
+                    if (hc[v] >= (1 << 23) || hc[v] <= -(1 << 23)) return QA_OK;  // coefficient does not fit the packed form
+                    H.ga[i] = (int32_t)((uint32_t)hg[v] | ((uint32_t)hc[v] << 8));
+                }
                 H.nlater[i] = (uint16_t)later.size();
                 H.deg[i] = (uint16_t)deg;
                 for (int part = 0; part < 2; ++part) {
@@ -1577,7 +1597,6 @@ int build_replay_tables(qa_model *M) {
                         int slot = 0;
                         if (wj != own) {
                             if (stamp[wj] != b) {
-                                if (nbw >= RP_MAXBW) return QA_OK;
                                 stamp[wj] = b;
                                 slot_of[wj] = nbw + 1;
                                 H.bw[nbw++] = wj;
@@ -1587,14 +1606,23 @@ int build_replay_tables(qa_model *M) {
                         RpEntry en;
                         en.J2 = 2.0 * nb.second;
                         en.j = j;
-                        en.B = (uint32_t)(31 - (j & 31)) | ((uint32_t)slot << 8) | ((j / RP_D) == b ? 0x8000u : 0u);
+                        en.B = (uint32_t)(31 - (j & 31)) | ((uint32_t)slot << 8) | ((j >= v0 && j < vmax) ? 0x4000u : 0u);
                         E.push_back(en);
                     }
                 }
                 H.row[i] = (uint32_t)start | ((uint32_t)(start + deg) << 16);
             }
+            // "neighbour inside the same block" is known only now that the block is closed
+            for (auto &en : E) {
+                const bool near = (en.B & 0x4000u) && en.j < v0 + nv;
+                en.B = (en.B & ~0xC000u) | (near ? 0x8000u : 0u);
+            }
+            for (int i = nv; i < RP_D; ++i) H.row[i] = (uint32_t)E.size() | ((uint32_t)E.size() << 16);
             H.nent = (int32_t)E.size();
             H.nbw = nbw;
+            H.v0 = v0;
+            H.nv = nv;
+            uniform = uniform && nv == RP_D;
             if (slabs.size() / 16 > 0xfffffff0ull) return QA_OK;
             off.push_back((uint32_t)(slabs.size() / 16));
             hdr_pos.push_back(slabs.size());
@@ -1602,11 +1630,14 @@ int build_replay_tables(qa_model *M) {
             slabs.insert(slabs.end(), hp, hp + sizeof(H));
             const unsigned char *ep = reinterpret_cast<const unsigned char *>(E.data());
             slabs.insert(slabs.end(), ep, ep + E.size() * sizeof(RpEntry));
+            v0 += nv;
         }
+        nslabs[p] = b;
+        if ((int64_t)b * 4 > (int64_t)npad) return QA_OK;   // fewer than 4 variables per block on average: replaying does not pay
         // every slab also carries the word list of the next block (cyclic) for the L2 run-ahead of its {S,F} rows
-        for (size_t b = 0; b < hdr_pos.size(); ++b) {
-            RpHdr *cur = reinterpret_cast<RpHdr *>(slabs.data() + hdr_pos[b]);
-            const RpHdr *nxt = reinterpret_cast<const RpHdr *>(slabs.data() + hdr_pos[(b + 1) % hdr_pos.size()]);
+        for (size_t k = 0; k < hdr_pos.size(); ++k) {
+            RpHdr *cur = reinterpret_cast<RpHdr *>(slabs.data() + hdr_pos[k]);
+            const RpHdr *nxt = reinterpret_cast<const RpHdr *>(slabs.data() + hdr_pos[(k + 1) % hdr_pos.size()]);
             cur->nbw_next = nxt->nbw;
             memcpy(cur->bw_next, nxt->bw, sizeof(cur->bw_next));
         }
@@ -1621,8 +1652,10 @@ int build_replay_tables(qa_model *M) {
     for (int p = 0; p < M->num_problems; ++p) {
         M->descs[p].rp_slabs = M->rp_slabs;
         M->descs[p].rp_off = M->rp_off + blk_base[p];
+        M->descs[p].rp_nslabs = nslabs[p];
     }
     M->rp_ok = true;
+    M->rp_uniform = uniform;
     return QA_OK;
 }
 
@@ -1775,8 +1808,13 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         const int64_t gpp = (tpp + nw - 1) / nw;
         const int64_t total_items = (int64_t)P * gpp;
         size_t smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
-        const void *fn = !groups ? (const void *)k_anneal_replay<0>
-                                 : (M->groups_i32 ? (const void *)k_anneal_replay<1> : (const void *)k_anneal_replay<2>);
+        const void *fn = nullptr;
+        if (M->rp_uniform)
+            fn = !groups ? (const void *)k_anneal_replay<0, false>
+                         : (M->groups_i32 ? (const void *)k_anneal_replay<1, false> : (const void *)k_anneal_replay<2, false>);
+        else
+            fn = !groups ? (const void *)k_anneal_replay<0, true>
+                         : (M->groups_i32 ? (const void *)k_anneal_replay<1, true> : (const void *)k_anneal_replay<2, true>);
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
         QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, nw * 32, smem, cudaOccupancyDefault));

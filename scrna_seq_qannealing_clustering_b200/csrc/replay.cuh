@@ -21,7 +21,8 @@
 // catch-up pass (pending u > v updates only) and finishes the schedule pushing, as neal does.  Both forms are exact, so
 // the hand-over point does not influence the result.
 //
-// Coupling slabs: for every block of RP_D variables the host builds one contiguous slab {RpHdr, RpEntry[]} (replay order,
+// Coupling slabs: the host packs consecutive variables greedily into blocks (at most RP_D variables, RP_MAXBW foreign spin
+// words, RP_CAP entries, never across a 32-variable spin word) and builds one contiguous slab {RpHdr, RpEntry[]} per block (replay order,
 // 2J premultiplied, slot/bit of the neighbour's spin word).  All warps of a CTA walk the blocks together; slabs are brought
 // into a 4-stage shared-memory ring with cp.async.bulk (TMA 1-D) completing on mbarriers, and released by one mbarrier arrive
 // per warp -- no __syncthreads in the sweep.  There is no fixed producer: whichever warp first gets within RP_DIST blocks of a
@@ -30,7 +31,7 @@
 #pragma once
 
 #ifndef RP_D
-#define RP_D 16       // variables per block (8 or 16)
+#define RP_D 16       // variables per block, at most
 #endif
 constexpr int RP_SLOTS = 2 * RP_D;            // spin-word slots per warp: slot 0 = the block's own word
 constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign spin words per block
@@ -40,7 +41,7 @@ constexpr int RP_STAGES = 4;      // power of two: stage = g & 3, phase = (g >> 
 #define RP_LA 2     // local fields are loaded this many variables ahead of their visit
 #endif
 #ifndef RP_PF_DIST
-#define RP_PF_DIST (32 / RP_D)   // L2 run-ahead of the field rows, in blocks
+#define RP_PF_DIST 32   // L2 run-ahead of the field rows, in variables
 #endif
 constexpr int RP_DIST = 2;        // slabs are requested this many blocks ahead of the first warp that will need them
 constexpr int RP_WARP_BYTES = RP_SLOTS * 32 * 8;  // per warp: {~S,F}[slot][lane]; the push phase stages its fields here
@@ -55,6 +56,8 @@ constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 8;
 struct alignas(16) RpHdr {
     int32_t nent;               // entries in this slab
     int32_t nbw;                // distinct neighbour words other than the block's own word
+    int32_t v0;                 // first variable of the block
+    int32_t nv;                 // variables in the block (1 .. RP_D; v0 .. v0+nv-1 lie in one 32-variable spin word)
     uint32_t row[RP_D];         // entry range of variable i: start | (end << 16)
     uint16_t nlater[RP_D];      // leading entries of row i that refer to later variables (u > v)
     uint16_t deg[RP_D];
@@ -64,7 +67,7 @@ struct alignas(16) RpHdr {
     int32_t bw_next[RP_MAXBW];
 };
 static_assert(sizeof(RpHdr) % 16 == 0, "slab header layout");
-constexpr uint32_t RP_H_NBW = offsetof(RpHdr, nbw), RP_H_ROW = offsetof(RpHdr, row), RP_H_NLATER = offsetof(RpHdr, nlater),
+constexpr uint32_t RP_H_NBW = offsetof(RpHdr, nbw), RP_H_V0 = offsetof(RpHdr, v0), RP_H_NV = offsetof(RpHdr, nv), RP_H_ROW = offsetof(RpHdr, row), RP_H_NLATER = offsetof(RpHdr, nlater),
                    RP_H_DEG = offsetof(RpHdr, deg), RP_H_GA = offsetof(RpHdr, ga), RP_H_BW = offsetof(RpHdr, bw),
                    RP_H_NBWN = offsetof(RpHdr, nbw_next), RP_H_BWN = offsetof(RpHdr, bw_next);
 struct __align__(16) RpEntry {
@@ -153,7 +156,7 @@ struct RpCtx {
     unsigned long long s0, s1;
     LaneStats st;
     bool active;
-    int n, nblk;
+    int n, nblk, npad;
 #ifdef QA_RP_PROFILE
     unsigned long long t_full, t_empty;  // cycles spent waiting for a slab / for a free stage
     unsigned long long t_setup, t_prol, t_ent, t_dec, t_pass, t_flip;
@@ -168,7 +171,7 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
         const unsigned old = atomicCAS(c.issued, cur, cur + 1u);
         if (old == cur) {
             int b = blk + (int)(cur - c.gb);
-            if (b >= c.nblk) b -= c.nblk;
+            while (b >= c.nblk) b -= c.nblk;
             const uint32_t st = cur & (RP_STAGES - 1), ph = (cur / RP_STAGES) & 1u;
 #ifdef QA_RP_PROFILE
             const long long t0 = clock64();
@@ -190,8 +193,10 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
 
 // One pass over all blocks.  MODE 0: replay sweep (pull).  MODE 1: catch-up (pending later-neighbour updates only, no
 // decisions).  MODE 2: push sweep (neal's eager form).  Returns the number of accepted flips of the warp.
-// GROUPS: 0 none, 1 rank-1 groups with 32-bit exact integer arithmetic (host-checked ranges), 2 with 64-bit
-template <int MODE, int GROUPS>
+// GROUPS: 0 none, 1 rank-1 groups with 32-bit exact integer arithmetic (host-checked ranges), 2 with 64-bit.
+// VAR: blocks of variable size (read from the slab header); false = every block holds exactly RP_D variables, which lets the
+// compiler keep the block geometry in immediates (22 % faster on config 3: the kernel sits at the 128-register limit).
+template <int MODE, int GROUPS, bool VAR>
 __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
     const int lane = threadIdx.x & 31;
     const double thr = 44.36142 / beta;
@@ -224,7 +229,8 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 #endif
         const uint32_t hdr = c.stage_s + stage * (uint32_t)RP_STAGE_BYTES;   // shared address of the slab
         const uint32_t ent = hdr + (uint32_t)sizeof(RpHdr);
-        const int v0 = blk * RP_D;
+        const int v0 = VAR ? (int)lds_u32(hdr + RP_H_V0) : blk * RP_D;
+        const int nv = VAR ? (int)lds_u32(hdr + RP_H_NV) : RP_D;
         const int wi = v0 >> 5;
         const int sub = v0 & 31;
         double *const fB = fT + (int64_t)v0 * 32;
@@ -234,8 +240,8 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
         }
 #ifndef RP_NO_PREFETCH
         {   // L2 run-ahead of the field rows RP_PF_DIST blocks on: 16 rows x 256 B = 128 sectors, one sector per lane and instruction
-            int pv = v0 + RP_PF_DIST * RP_D;
-            if (pv >= nblk * RP_D) pv -= nblk * RP_D;
+            int pv = (v0 & ~(RP_D - 1)) + RP_PF_DIST;   // a 16-row group ahead (wraps into the next sweep)
+            if (pv >= c.npad) pv -= c.npad;
             const char *pa = reinterpret_cast<const char *>(fT - lane + (int64_t)pv * 32) + lane * 32;
 #pragma unroll
             for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + k * 1024));
@@ -247,7 +253,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                 const int64_t w = (int64_t)lds_u32(hdr + RP_H_BWN + 4u * (uint32_t)(k >> 3));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + w * 256 + (k & 7) * 32));
             }
-            if (sub != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + (int64_t)(wi + 1 < nblk / 2 ? wi + 1 : 0) * 256 + (lane & 7) * 32));
+            if (sub != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + (int64_t)((wi + 1) * 32 < c.npad ? wi + 1 : 0) * 256 + (lane & 7) * 32));
         }
 #endif
         bool blk_dirty = false;
@@ -267,18 +273,21 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
         } else {
             double t[RP_D];
 #pragma unroll
-            for (int i = 0; i < RP_D; ++i) t[i] = __ldcg(fB + i * 32);
+            for (int i = 0; i < RP_D; ++i)
+                if (i < nv) t[i] = __ldcg(fB + i * 32);
 #pragma unroll
-            for (int i = 0; i < RP_D; ++i) sts_f64(sfb + (uint32_t)i * 256u, t[i]);
+            for (int i = 0; i < RP_D; ++i)
+                if (i < nv) sts_f64(sfb + (uint32_t)i * 256u, t[i]);
         }
         double fq[RP_LA];   // fields of the next RP_LA variables, loaded ahead of their visit
 #pragma unroll
         for (int k = 0; k < RP_LA; ++k) fq[k] = 0.0;
         if (MODE <= 1) {
 #pragma unroll
-            for (int k = 0; k < RP_LA; ++k) fq[k] = __ldcg(fB + k * 32);
+            for (int k = 0; k < RP_LA; ++k)
+                if (k < nv) fq[k] = __ldcg(fB + k * 32);
         }
-        const int ilim = min(RP_D, n - v0);   // uniform: padding variables are not visited
+        const int ilim = min(nv, n - v0);   // uniform: padding variables are not visited
 #ifdef QA_RP_PROFILE
         c.t_prol += (unsigned long long)(clock64() - tw0) ;
 #endif
@@ -293,7 +302,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                 fv = fq[0];
 #pragma unroll
                 for (int k = 0; k + 1 < RP_LA; ++k) fq[k] = fq[k + 1];
-                if (i + RP_LA < RP_D) fq[RP_LA - 1] = __ldcg(fB + (i + RP_LA) * 32);
+                if (i + RP_LA < nv) fq[RP_LA - 1] = __ldcg(fB + (i + RP_LA) * 32);
                 const double f0 = fv;
 #ifdef QA_RP_PROFILE
                 const long long te0 = clock64();
@@ -392,7 +401,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                     const int4 q = lds_v4(ad);
                     const double d = __hiloint2double(q.y ^ sgn, q.x);
                     if ((uint32_t)q.w & 0x8000u) {   // uniform: neighbour staged in this block
-                        const uint32_t ca = sfb + (((uint32_t)q.z & (uint32_t)(RP_D - 1)) << 8);
+                        const uint32_t ca = sfb + ((uint32_t)(q.z - v0) << 8);
                         if (acc) sts_f64(ca, lds_f64(ca) + d);
                         blk_dirty = true;
                     } else {
@@ -415,10 +424,11 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
         if (MODE == 2) {
             if (blk_dirty) {  // uniform: write the staged fields back (coalesced 256 B rows)
 #pragma unroll
-                for (int i = 0; i < RP_D; ++i) __stcg(fB + i * 32, lds_f64(sfb + (uint32_t)i * 256u));
+                for (int i = 0; i < RP_D; ++i)
+                    if (i < nv) __stcg(fB + i * 32, lds_f64(sfb + (uint32_t)i * 256u));
             }
         }
-        if (MODE != 1 && sub + RP_D == 32) {
+        if (MODE != 1 && sub + nv == 32) {
             if (S != S0 || F != F0) __stcg(SF + (int64_t)wi * 32, make_uint2(S, F));
         }
         // release the stage: one arrive per warp
@@ -470,7 +480,7 @@ __host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned
 }
 constexpr int QA_ERR_SMEM_BASE = -100;   // internal: the dynamic shared memory does not start where the host assumed
 
-template <int GROUPS>
+template <int GROUPS, bool VAR>
 __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_replay(AnnealParams P) {
     extern __shared__ __align__(16) unsigned char rp_raw[];
     const int lane = threadIdx.x & 31;
@@ -555,7 +565,8 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
         const long long cta_reads = min((long long)NW * 32, (long long)D.reads - (long long)q * NW * 32);
         c.active = active;
         c.n = D.n;
-        c.nblk = D.nch * (32 / RP_D);
+        c.nblk = D.rp_nslabs;
+        c.npad = D.nch * 32;
         c.slabs = D.rp_slabs;
         c.off = D.rp_off;
         const long long total_sweeps = (long long)P.num_betas * P.sweeps_per_beta;
@@ -621,9 +632,9 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                     printf("[qa sweep] %lld beta %.4g mode %s clock %lld\n", done, beta, push ? "push" : "replay", clock64());
 #endif
                 if (push) {
-                    rp_pass<2, GROUPS>(c, beta, more);
+                    rp_pass<2, GROUPS, VAR>(c, beta, more);
                 } else {
-                    const unsigned wacc = rp_pass<0, GROUPS>(c, beta, more);
+                    const unsigned wacc = rp_pass<0, GROUPS, VAR>(c, beta, more);
                     if (more) {  // CTA-uniform hand-over decision
                         if (lane == 0) atomicAdd(acc_sh + acc_par, wacc);
                         __syncthreads();
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                         if (threadIdx.x == 0) acc_sh[acc_par ^ 1] = 0u;
                         acc_par ^= 1;
                         if (tot * 1000ull < (unsigned long long)P.switch_permille * (unsigned long long)n * (unsigned long long)cta_reads) {
-                            rp_pass<1, 0>(c, beta, true);
+                            rp_pass<1, 0, VAR>(c, beta, true);
                             push = true;
                         }
                     }

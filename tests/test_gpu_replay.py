@@ -43,10 +43,10 @@ def _replay_ctx(permille=None, warps=None):
     return ctx
 
 
-def _check(ctx, model, R, sweeps, seed, beta_range=(0.05, 8.0), expect_replay=True):
+def _check(ctx, model, R, sweeps, seed, beta_range=(0.05, 8.0), expect_replay=True, spb=1):
     n = model.num_variables
     groups = model.groups.astuple() if model.groups is not None else None
-    betas, spb = schedule.make_beta_schedule(beta_range, sweeps, 1, "geometric")
+    betas, spb = schedule.make_beta_schedule(beta_range, sweeps, spb, "geometric")
     seeds = schedule.per_read_seeds(seed, R)
     init = schedule.random_spin_states(R, n, seed)
     ref = init.copy()
@@ -168,3 +168,28 @@ def test_batch_of_independent_problems(built):
         off += rpp * m.num_variables
         assert np.array_equal(got, ref)
         assert np.array_equal(e[i * rpp:(i + 1) * rpp].view(np.uint64), ref_e.view(np.uint64))
+
+
+def test_large_group_coefficients_take_the_64_bit_path(built, graph256):
+    """a * (a - s (M + kappa)) exceeds 2^31 for |a| = 50 000: the kernel instance with 64-bit group arithmetic runs."""
+    base = models.subsampling_model(graph256, 7.0)
+    n = base.num_variables
+    rng = np.random.default_rng(3)
+    grp = np.where(np.arange(n) % 3 == 0, 0, np.where(np.arange(n) % 3 == 1, 1, -1)).astype(np.int32)
+    coef = rng.choice(np.array([1, -3, 50000, -47000], dtype=np.int32), size=n).astype(np.int32)
+    coef[grp < 0] = 0
+    groups = models.Groups(grp, coef, np.array([1e-9, 2.5e-10]), np.array([12345, -777], dtype=np.int64))
+    m = models.LoweredModel(base.h, base.starts, base.ends, base.weights, 0.0, base.labels, groups=groups)
+    ctx = _replay_ctx()
+    try:
+        _check(ctx, m, 100, 80, 4, beta_range=(0.02, 6.0))
+    finally:
+        ctx.close()
+
+
+def test_several_sweeps_per_beta(built, graph256):
+    ctx = _replay_ctx(permille=80)
+    try:
+        _check(ctx, models.subsampling_model(graph256, 7.0), 64, 30, 12, spb=3)
+    finally:
+        ctx.close()
