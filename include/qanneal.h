@@ -172,6 +172,20 @@ int qa_build_cqm_penalty(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t 
                          int32_t num_clusters, int32_t min_size, double onehot_penalty, double size_penalty, qa_model **out,
                          double *offset_out);
 
+/* ---- SampleSet post-processing on the device (what the reference does with a SampleSet after the call:
+ * energy-sorted iteration and k-th best energies BQM_clustering.py:93-146, the 16 best samples plot_and_save.py:105-126,
+ * one-hot decode of DQM / CQM samples plot_and_save.py:46-63).  Pointers may be host or device memory. ---- */
+/* order_out[r] = index of the r-th best read: ascending energy, ties in read order (stable) */
+int qa_sort_reads(qa_ctx *ctx, int32_t num_reads, const double *energies, int32_t *order_out);
+/* samples_out[r][0..n) = states[order[r]][0..n) for r < k: only the k best samples leave the device */
+int qa_gather_samples(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *states, int32_t k, const int32_t *order,
+                      int8_t *samples_out);
+/* one-hot decode: variable (cell i, case c) = states[read][i*K + c] (stride >= cells*K bytes per read; on_value = +1 for
+ * spins, 1 for binaries).  labels_out[read][cell] = case or -1 when the cell is not one-hot;
+ * violations_out[read] = {cells that are not one-hot, cases with fewer than min_size cells} */
+int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int32_t num_reads, const int8_t *states,
+                     int32_t on_value, int32_t min_size, int32_t *labels_out, int32_t *violations_out);
+
 #ifdef __cplusplus
 }
 #endif

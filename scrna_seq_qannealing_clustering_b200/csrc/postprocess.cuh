@@ -1,0 +1,163 @@
+// postprocess.cuh -- SampleSet post-processing on the device.  Included by qanneal.cu.
+//
+// What the reference does with a SampleSet after the sampler call (all on the host, one sample at a time):
+//   response.data(fields=['sample','energy','num_occurrences'])  -- energy-sorted iteration       BQM_clustering.py:93,281,397
+//   response.record.energy[0] / [3]                              -- k-th best energy              BQM_clustering.py:133-146
+//   sampleset.samples()[:16]                                      -- the 16 best samples           plot_and_save.py:105-126
+//   sample[(i, c)] / 'v_i,c' == 1 -> label                        -- one-hot decode of DQM / CQM   plot_and_save.py:46-63
+// With 10^5 reads of 10^5 variables the int8 state matrix is 13 GB: ordering, picking and decoding on the device means only
+// the k best samples (and the labels) cross PCIe.
+#pragma once
+
+namespace {
+
+// order-preserving map double -> uint64 (ascending); NaNs sort last
+__global__ void k_energy_keys(int32_t count, const double *e, unsigned long long *keys, int32_t *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long b = (unsigned long long)__double_as_longlong(e[i] + 0.0);   // -0.0 and +0.0 tie
+    b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    keys[i] = b;
+    idx[i] = i;
+}
+
+// samples_out[r] = states[order[r]] for r < k  (one block per output row, coalesced 16-byte copies when aligned)
+__global__ void k_gather_rows(int32_t n, const int8_t *states, const int32_t *order, int8_t *out) {
+    const int8_t *src = states + (int64_t)order[blockIdx.x] * n;
+    int8_t *dst = out + (int64_t)blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// one thread per (read, cell): label = the single case whose bit is set, -1 if the cell is not one-hot
+__global__ void k_decode_onehot(int32_t cells, int32_t K, int64_t stride, int32_t reads, const int8_t *states, int32_t on_value,
+                                int32_t *labels, int32_t *sizes, int32_t *violations) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)reads * cells) return;
+    const int32_t r = (int32_t)(t / cells), c = (int32_t)(t % cells);
+    const int8_t *row = states + (int64_t)r * stride + (int64_t)c * K;
+    int cnt = 0, lab = -1;
+    for (int k = 0; k < K; ++k)
+        if (row[k] == on_value) { ++cnt; lab = k; }
+    if (cnt != 1) {
+        lab = -1;
+        atomicAdd(violations + 2 * r, 1);
+    } else {
+        atomicAdd(sizes + (int64_t)r * K + lab, 1);
+    }
+    labels[t] = lab;
+}
+
+__global__ void k_count_small_clusters(int32_t reads, int32_t K, int32_t min_size, const int32_t *sizes, int32_t *violations) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= reads) return;
+    int bad = 0;
+    for (int k = 0; k < K; ++k) bad += sizes[(int64_t)r * K + k] < min_size;
+    violations[2 * r + 1] = bad;
+}
+
+// stage `bytes` of a caller buffer (host or device) on the device; returns the device pointer to use
+int stage_in(qa_ctx *ctx, DevBuf &buf, const void *p, size_t bytes, const void **dev) {
+    if (is_device_ptr(p)) { *dev = p; return QA_OK; }
+    int rc = ensure(buf, bytes);
+    if (rc) return rc;
+    QA_CUDA(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = buf.p;
+    return QA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qa_sort_reads(qa_ctx *ctx, int32_t num_reads, const double *energies, int32_t *order_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (num_reads < 0) return fail(QA_ERR_ARG, "negative num_reads");
+    if (num_reads == 0) return QA_OK;
+    if (!energies || !order_out) return fail(QA_ERR_ARG, "null energies / order");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const void *d_e = nullptr;
+    int rc = stage_in(ctx, ctx->energies, energies, (size_t)num_reads * sizeof(double), &d_e);
+    if (rc) return rc;
+    // scratch: keys, keys2 (u64), idx, idx2 (i32)
+    const size_t kb = (size_t)num_reads * sizeof(unsigned long long), ib = (size_t)num_reads * sizeof(int32_t);
+    rc = ensure(ctx->misc, 2 * kb + 2 * ib + 64);
+    if (rc) return rc;
+    unsigned long long *keys = (unsigned long long *)ctx->misc.p, *keys2 = keys + num_reads;
+    int32_t *idx = (int32_t *)(keys2 + num_reads), *idx2 = idx + num_reads;
+    k_energy_keys<<<(num_reads + 255) / 256, 256, 0, ctx->stream>>>(num_reads, (const double *)d_e, keys, idx);
+    ctx->launches++;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys2, idx, idx2, num_reads, 0, 64, ctx->stream);
+    rc = ensure(ctx->cubtmp, tmp);
+    if (rc) return rc;
+    cudaError_t ce = cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, tmp, keys, keys2, idx, idx2, num_reads, 0, 64, ctx->stream);
+    if (ce != cudaSuccess) return fail(QA_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(ce));
+    ctx->launches += 8;
+    QA_CUDA(cudaMemcpyAsync(order_out, idx2, ib, cudaMemcpyDefault, ctx->stream));   // radix sort is stable: ties keep read order
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_gather_samples(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *states, int32_t k, const int32_t *order,
+                      int8_t *samples_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (n < 0 || num_reads < 0 || k < 0) return fail(QA_ERR_ARG, "negative size");
+    if (k == 0 || n == 0) return QA_OK;
+    if (!states || !order || !samples_out) return fail(QA_ERR_ARG, "null states / order / samples_out");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int32_t> ho(k);
+    QA_CUDA(cudaMemcpy(ho.data(), order, (size_t)k * sizeof(int32_t), cudaMemcpyDefault));
+    for (int32_t r : ho)
+        if (r < 0 || r >= num_reads) return fail(QA_ERR_INDEX, "order entry out of range");
+    if (!is_device_ptr(states)) {   // host matrix: nothing to gain from the device, copy the rows directly
+        for (int32_t r = 0; r < k; ++r)
+            QA_CUDA(cudaMemcpy(samples_out + (int64_t)r * n, states + (int64_t)ho[r] * n, (size_t)n, cudaMemcpyDefault));
+        return QA_OK;
+    }
+    int rc = ensure(ctx->seeds, (size_t)k * sizeof(int32_t));
+    if (rc) return rc;
+    QA_CUDA(cudaMemcpyAsync(ctx->seeds.p, ho.data(), (size_t)k * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    int8_t *d_out = samples_out;
+    const bool out_host = !is_device_ptr(samples_out);
+    if (out_host) {
+        rc = ensure(ctx->packed, (size_t)k * n);
+        if (rc) return rc;
+        d_out = (int8_t *)ctx->packed.p;
+    }
+    k_gather_rows<<<k, 256, 0, ctx->stream>>>(n, states, (const int32_t *)ctx->seeds.p, d_out);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (out_host) QA_CUDA(cudaMemcpyAsync(samples_out, d_out, (size_t)k * n, cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int32_t num_reads, const int8_t *states,
+                     int32_t on_value, int32_t min_size, int32_t *labels_out, int32_t *violations_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (cells < 0 || K < 1 || num_reads < 0 || stride < (int64_t)cells * K) return fail(QA_ERR_ARG, "bad one-hot geometry");
+    if (num_reads == 0 || cells == 0) return QA_OK;
+    if (!states || !labels_out || !violations_out) return fail(QA_ERR_ARG, "null states / labels / violations");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const void *d_states = nullptr;
+    int rc = stage_in(ctx, ctx->states, states, (size_t)num_reads * stride, &d_states);
+    if (rc) return rc;
+    const size_t lb = (size_t)num_reads * cells * sizeof(int32_t), sb = (size_t)num_reads * K * sizeof(int32_t),
+                 vb = (size_t)num_reads * 2 * sizeof(int32_t);
+    rc = ensure(ctx->misc, lb + sb + vb + 64);
+    if (rc) return rc;
+    int32_t *d_lab = (int32_t *)ctx->misc.p, *d_sizes = d_lab + (size_t)num_reads * cells, *d_viol = d_sizes + (size_t)num_reads * K;
+    QA_CUDA(cudaMemsetAsync(d_sizes, 0, sb + vb, ctx->stream));
+    const int64_t total = (int64_t)num_reads * cells;
+    k_decode_onehot<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(cells, K, stride, num_reads, (const int8_t *)d_states,
+                                                                               on_value, d_lab, d_sizes, d_viol);
+    k_count_small_clusters<<<(num_reads + 255) / 256, 256, 0, ctx->stream>>>(num_reads, K, min_size, d_sizes, d_viol);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    QA_CUDA(cudaMemcpyAsync(labels_out, d_lab, lb, cudaMemcpyDefault, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(violations_out, d_viol, vb, cudaMemcpyDefault, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+}  // extern "C"

@@ -2670,3 +2670,5 @@ int qa_build_dqm_onehot(qa_ctx *ctx, int32_t n, int64_t m, const int32_t *eu, co
 }
 
 }  // extern "C"
+
+#include "postprocess.cuh"

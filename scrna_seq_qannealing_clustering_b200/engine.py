@@ -70,6 +70,39 @@ class Context:
     def synchronize(self):
         check(_lib.load().qa_ctx_synchronize(self._h))
 
+    # -- SampleSet post-processing on the device (include/qanneal.h; reference consumption: BQM_clustering.py:93-146,
+    #    plot_and_save.py:46-63, 105-126).  Arrays may be numpy (host) or torch CUDA tensors. ---
+    def sort_reads(self, energies):
+        """Read indices by ascending energy, ties in read order (what ``SampleSet.data(sorted_by='energy')`` iterates)."""
+        num_reads = int(energies.shape[0])
+        if not _is_tensor(energies):
+            energies = np.ascontiguousarray(energies, dtype=np.float64)
+        order = np.empty(num_reads, dtype=np.int32)
+        check(_lib.load().qa_sort_reads(self._h, num_reads, ptr(energies), ptr(order)))
+        return order
+
+    def gather_samples(self, states, order):
+        """``states[order]`` as a host array: only the selected rows leave the device."""
+        num_reads, n = int(states.shape[0]), int(states.shape[1])
+        if not _is_tensor(states):
+            states = np.ascontiguousarray(states, dtype=np.int8)
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        out = np.empty((len(order), n), dtype=np.int8)
+        check(_lib.load().qa_gather_samples(self._h, n, num_reads, ptr(states), len(order), ptr(order), ptr(out)))
+        return out
+
+    def decode_onehot(self, states, cells: int, num_cases: int, on_value: int = 1, min_size: int = 0):
+        """Labels of a DQM / CQM sample matrix: ``labels[read][cell]`` (-1: the cell is not one-hot) and per read the number of
+        cells that are not one-hot and of cases with fewer than ``min_size`` cells (CQM_clustering.py:44-48)."""
+        num_reads, stride = int(states.shape[0]), int(states.shape[1])
+        if not _is_tensor(states):
+            states = np.ascontiguousarray(states, dtype=np.int8)
+        labels = np.empty((num_reads, cells), dtype=np.int32)
+        violations = np.empty((num_reads, 2), dtype=np.int32)
+        check(_lib.load().qa_decode_onehot(self._h, int(cells), int(num_cases), stride, num_reads, ptr(states), int(on_value),
+                                           int(min_size), ptr(labels), ptr(violations)))
+        return labels, violations
+
     # -- model construction on the device (qa_build_*): graph = (n, eu, ev, w) in G.edges order ---
     def _graph_args(self, graph):
         n, eu, ev, w = graph

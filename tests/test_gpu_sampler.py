@@ -155,3 +155,49 @@ def test_throughput_mode_through_the_sampler(sampler):
     known = json.loads((GOLD / "known_answers.json").read_text())["noisy_circles"]
     assert ss.first.energy == pytest.approx(known["lower_bound"], rel=1e-10)
     assert np.allclose(ss.record.energy, model.energies(2 * ss.record.sample.astype(np.int64) - 1), rtol=1e-12, atol=1e-8)
+
+
+# ---- SampleSet post-processing on the device (qa_sort_reads / qa_gather_samples / qa_decode_onehot) --------------------
+def test_device_sort_topk_and_onehot_decode(built):
+    from scrna_seq_qannealing_clustering_b200.engine import Context
+    rng = np.random.default_rng(5)
+    R, cells, K, slack = 3000, 37, 4, 11
+    energies = np.round(rng.normal(size=R), 1)          # many ties: the order must be stable
+    energies[7] = -np.inf
+    energies[11] = np.inf
+    onehot = rng.integers(0, K, size=(R, cells))
+    states = -np.ones((R, cells * K + slack), dtype=np.int8)
+    for c in range(cells):
+        states[np.arange(R), c * K + onehot[:, c]] = 1
+    states[5, 0:K] = 1                                   # read 5: cell 0 has four bits set
+    states[6, K:2 * K] = -1                              # read 6: cell 1 has none
+    states[:, cells * K:] = rng.choice(np.array([-1, 1], dtype=np.int8), size=(R, slack))
+    with Context(0) as ctx:
+        order = ctx.sort_reads(energies)
+        assert np.array_equal(order, np.argsort(energies, kind="stable"))
+        best = ctx.gather_samples(states, order[:16])
+        assert np.array_equal(best, states[order[:16]])
+        labels, viol = ctx.decode_onehot(states, cells, K, on_value=1, min_size=700)
+        if torch_cuda():
+            import torch
+            d_states = torch.from_numpy(states).cuda()
+            d_e = torch.from_numpy(energies).cuda()
+            assert np.array_equal(ctx.sort_reads(d_e), order)
+            assert np.array_equal(ctx.gather_samples(d_states, order[:16]), best)
+            l2, v2 = ctx.decode_onehot(d_states, cells, K, on_value=1, min_size=700)
+            assert np.array_equal(l2, labels) and np.array_equal(v2, viol)
+    want = onehot.astype(np.int32).copy()
+    want[5, 0] = -1
+    want[6, 1] = -1
+    assert np.array_equal(labels, want)
+    not_onehot = (want < 0).sum(axis=1)
+    sizes = np.stack([(want == k).sum(axis=1) for k in range(K)], axis=1)
+    assert np.array_equal(viol[:, 0], not_onehot) and np.array_equal(viol[:, 1], (sizes < 700).sum(axis=1))
+
+
+def torch_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
