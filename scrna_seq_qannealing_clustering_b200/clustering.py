@@ -170,3 +170,75 @@ def disconnected_components(G):
             for n in s.nodes():
                 G.nodes[n]["valid"] = 0
     return G, S, lengths
+
+
+def recursive_bipartition_batched(G, gamma_factor, k=8.0, size_limit=40, iter_limit=2, num_reads=64, num_sweeps=200,
+                                  beta_range=None, seed=None, context=None, model="cut_balance"):
+    """Level-synchronous form of the recursion in ``clustering_bqm`` / ``clustering_bqm_2`` (BQM_clustering.py:113-203,
+    302-350, termination rule ``min_size``): instead of one sampler call per sub-graph, ALL sub-graphs of a recursion level
+    are annealed as one batch of independent problems in a single launch (``qa_sa_sample_ising_batch``, the launch behind
+    QA_subsampling's config 4).
+
+    Every sub-graph gets the reference's model -- ``model="cut_balance"``: ``clustering_bqm``'s Q (k * cut + gamma * s(s - n),
+    materialised: the batched launch carries explicit couplers only, so this is meant for sub-graphs of up to a few thousand
+    cells); ``model="cut_linear"``: ``clustering_bqm_2``'s sparse Q (k * cut + gamma * sum x) -- ``num_reads`` reads with
+    per-read seeds and one beta schedule per level; its lowest-energy read splits it (``response.first``), and both halves go
+    to the next level while they are larger than ``size_limit`` and the level is below ``iter_limit``.
+    Returns ``{node: leaf index}``, the list of levels (each a list of node lists) and the per-level best energies.
+    """
+    from . import schedule
+    from .engine import Context
+
+    own_ctx = context is None
+    ctx = Context(0) if own_ctx else context
+    try:
+        frontier = [list(G.nodes)]
+        leaves, levels, level_energies = [], [], []
+        iteration = 0
+        rng_seed = 0 if seed is None else int(seed)
+        while frontier:
+            levels.append(frontier)
+            if model == "cut_balance":
+                ms = [models.cut_balance_model(G.subgraph(nodes), gamma_factor, k=k, structured=False) for nodes in frontier]
+            elif model == "cut_linear":
+                ms = [models.cut_linear_model(G.subgraph(nodes), gamma_factor, k) for nodes in frontier]
+            else:
+                raise ValueError("model must be 'cut_balance' or 'cut_linear'")
+            br = beta_range
+            if br is None:   # one schedule for the whole level: the widest range any of its problems asks for
+                rs = [schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights) for m in ms if m.num_couplers > 0]
+                br = (min(r[0] for r in rs), max(r[1] for r in rs)) if rs else (0.1, 1.0)
+            betas, spb = schedule.make_beta_schedule(br, num_sweeps, 1, "geometric")
+            voff = np.cumsum([0] + [m.num_variables for m in ms])
+            coff = np.cumsum([0] + [m.num_couplers for m in ms])
+            seeds = schedule.per_read_seeds(rng_seed + 7919 * iteration, num_reads * len(ms))
+            states = np.concatenate([schedule.random_spin_states(num_reads, m.num_variables, rng_seed + 31 * iteration + i).ravel()
+                                     for i, m in enumerate(ms)])
+            e, _, done = ctx.sample_ising_batch(voff, coff, np.concatenate([m.h for m in ms]),
+                                                np.concatenate([m.starts for m in ms]), np.concatenate([m.ends for m in ms]),
+                                                np.concatenate([m.weights for m in ms]), num_reads, states, betas, spb, seeds)
+            assert done == num_reads
+            nxt, best = [], []
+            off = 0
+            for i, (nodes, m) in enumerate(zip(frontier, ms)):
+                n = m.num_variables
+                rows = states[off:off + num_reads * n].reshape(num_reads, n)
+                off += num_reads * n
+                ei = e[i * num_reads:(i + 1) * num_reads]
+                b = int(np.argmin(ei))          # first minimum == SampleSet.first of an energy-sorted, stable record
+                best.append(float(ei[b] + m.offset))
+                S0 = [lab for lab, s in zip(m.labels, rows[b]) if s < 0]     # x = 0
+                S1 = [lab for lab, s in zip(m.labels, rows[b]) if s > 0]     # x = 1
+                go = len(S0) > size_limit and len(S1) > size_limit and iteration < iter_limit
+                for part in (S0, S1):
+                    if not part:
+                        continue
+                    (nxt if go else leaves).append(part)
+            level_energies.append(best)
+            frontier = nxt
+            iteration += 1
+        labels = {node: idx for idx, part in enumerate(leaves) for node in part}
+        return labels, levels, level_energies
+    finally:
+        if own_ctx:
+            ctx.close()
