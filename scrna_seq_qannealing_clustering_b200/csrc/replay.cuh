@@ -241,7 +241,8 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 #ifndef RP_NO_PREFETCH
         {   // L2 run-ahead of the field rows RP_PF_DIST blocks on: 16 rows x 256 B = 128 sectors, one sector per lane and instruction
             int pv = (v0 & ~(RP_D - 1)) + RP_PF_DIST;   // a 16-row group ahead (wraps into the next sweep)
-            if (pv >= c.npad) pv -= c.npad;
+            const int npad = VAR ? c.npad : nblk * RP_D;
+            if (pv >= npad) pv -= npad;
             const char *pa = reinterpret_cast<const char *>(fT - lane + (int64_t)pv * 32) + lane * 32;
 #pragma unroll
             for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + k * 1024));
@@ -253,7 +254,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                 const int64_t w = (int64_t)lds_u32(hdr + RP_H_BWN + 4u * (uint32_t)(k >> 3));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + w * 256 + (k & 7) * 32));
             }
-            if (sub != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + (int64_t)((wi + 1) * 32 < c.npad ? wi + 1 : 0) * 256 + (lane & 7) * 32));
+            if (sub != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + (int64_t)((wi + 1) * 32 < (VAR ? c.npad : nblk * RP_D) ? wi + 1 : 0) * 256 + (lane & 7) * 32));
         }
 #endif
         bool blk_dirty = false;
