@@ -186,6 +186,12 @@ int qa_gather_samples(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *s
 int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int32_t num_reads, const int8_t *states,
                      int32_t on_value, int32_t min_size, int32_t *labels_out, int32_t *violations_out);
 
+/* Test hook, host only (no device needed): the coupling slabs the replay kernel would get for a CSR in host memory
+ * (adjacency order).  Returns 1 when the model fits the slab format, 0 when it does not, < 0 on error. */
+int qa_debug_pack_slabs(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, int32_t ngroups,
+                        const int32_t *grp, const int32_t *coef, int64_t *nslabs_out, int64_t *bytes_out, int32_t *uniform_out,
+                        unsigned char *slabs_out, uint32_t *off_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,4 +160,33 @@ int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int3
     return QA_OK;
 }
 
+/* Test hook, host only (no device needed): pack the replay kernel's coupling slabs for one problem whose CSR (adjacency order,
+ * rowptr[n + 1], col, val) is in host memory.  Returns 1 when the model fits the slab format (0: it does not, negative: error);
+ * on success *nslabs_out / *bytes_out / *uniform_out are set and, when the buffers are given (bytes_out reports the size to
+ * allocate), slabs_out receives the serialized slabs and off_out[nslabs + 1] their offsets in 16-byte units. */
+int qa_debug_pack_slabs(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, int32_t ngroups,
+                        const int32_t *grp, const int32_t *coef, int64_t *nslabs_out, int64_t *bytes_out, int32_t *uniform_out,
+                        unsigned char *slabs_out, uint32_t *off_out) {
+    if (n < 1 || !rowptr || !nslabs_out || !bytes_out || !uniform_out) return fail(QA_ERR_ARG, "bad arguments");
+    const int64_t npad = ((int64_t)n + 31) / 32 * 32;
+    std::vector<int32_t> rp(npad + 1);
+    for (int64_t v = 0; v <= npad; ++v) rp[v] = rowptr[std::min<int64_t>(v, n)];
+    std::vector<int32_t> hg, hc;
+    if (ngroups > 0) {
+        if (!grp || !coef) return fail(QA_ERR_ARG, "null group vectors");
+        hg.assign(npad, -1);
+        hc.assign(npad, 0);
+        for (int32_t v = 0; v < n; ++v) { hg[v] = grp[v]; hc[v] = coef[v]; }
+    }
+    const int64_t var_off[2] = {0, n};
+    RpPacked pk;
+    if (!pack_replay_slabs(1, var_off, rp.data(), col, val, ngroups, hg, hc, pk)) return 0;
+    *nslabs_out = pk.nslabs[0];
+    *bytes_out = (int64_t)pk.slabs.size();
+    *uniform_out = pk.uniform ? 1 : 0;
+    if (slabs_out) memcpy(slabs_out, pk.slabs.data(), pk.slabs.size());
+    if (off_out) memcpy(off_out, pk.off.data(), pk.off.size() * sizeof(uint32_t));
+    return 1;
+}
+
 }  // extern "C"

@@ -1503,43 +1503,37 @@ int build_word_tables(qa_model *M) {
 // variables, RP_CAP entries and RP_MAXBW foreign spin words, never across a 32-variable spin word.  Models whose blocks would
 // hold fewer than 4 variables on average (dense rows, or sparse rows scattered over many words) leave rp_ok false and run on
 // the other kernels.
-int build_replay_tables(qa_model *M) {
-    if (M->rp_built) return QA_OK;
-    qa_ctx *ctx = M->ctx;
-    M->rp_built = true;
-    M->rp_ok = false;
-    const int64_t entries = 2 * M->m_total;
-    const int64_t rows_alloc = M->n_total + 64 + 1;
-    QA_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int32_t> rowptr(rows_alloc), col(std::max<int64_t>(entries, 1));
-    std::vector<double> val(std::max<int64_t>(entries, 1));
-    QA_CUDA(cudaMemcpy(rowptr.data(), M->rowptr, rows_alloc * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    if (entries) {
-        QA_CUDA(cudaMemcpy(col.data(), M->col, entries * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        QA_CUDA(cudaMemcpy(val.data(), M->val, entries * sizeof(double), cudaMemcpyDeviceToHost));
-    }
-    std::vector<int32_t> hg, hc;
-    if (M->ngroups > 0) {
-        const int64_t npad = (int64_t)M->descs[0].nch * 32;
-        hg.resize(npad);
-        hc.resize(npad);
-        QA_CUDA(cudaMemcpy(hg.data(), M->grp, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        QA_CUDA(cudaMemcpy(hc.data(), M->coef, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    }
-    std::vector<uint32_t> off;
+// Pure host part of the slab construction (no CUDA calls: the CPU test-suite drives it through qa_debug_pack_slabs).
+// rowptr holds global entry positions per global row (problem p's rows start at var_off[p]), col local neighbour indices.
+struct RpPacked {
+    std::vector<uint32_t> off;          // slab offsets in 16-byte units, one terminator
     std::vector<unsigned char> slabs;
-    std::vector<int64_t> blk_base(M->num_problems, 0);
+    std::vector<int64_t> blk_base;      // first slab of every problem in `off`
+    std::vector<int32_t> nslabs;
+    bool uniform = true;                // every block holds exactly RP_D variables
+};
+
+bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, const int32_t *col, const double *val, int ngroups,
+                       const std::vector<int32_t> &hg, const std::vector<int32_t> &hc, RpPacked &out) {
+    std::vector<uint32_t> &off = out.off;
+    std::vector<unsigned char> &slabs = out.slabs;
+    std::vector<int64_t> &blk_base = out.blk_base;
+    std::vector<int32_t> &nslabs = out.nslabs;
+    bool &uniform = out.uniform;
+    off.clear();
+    slabs.clear();
+    blk_base.assign(P, 0);
+    nslabs.assign(P, 0);
+    uniform = true;
     std::vector<int32_t> stamp, slot_of;
     std::vector<std::pair<int32_t, double>> later, earlier;
     std::vector<RpEntry> E;
     std::vector<size_t> hdr_pos;
-    std::vector<int32_t> nslabs(M->num_problems, 0);
-    bool uniform = true;
     std::vector<int32_t> row_words;
-    for (int p = 0; p < M->num_problems; ++p) {
-        const int64_t v_off = M->var_off[p];
-        const int n = (int)(M->var_off[p + 1] - v_off);
-        if (n == 0) return QA_OK;
+    for (int p = 0; p < P; ++p) {
+        const int64_t v_off = var_off[p];
+        const int n = (int)(var_off[p + 1] - v_off);
+        if (n == 0) return false;
         const int nch = (n + 31) / 32;
         const int npad = nch * 32;
         blk_base[p] = (int64_t)off.size();
@@ -1579,13 +1573,13 @@ int build_replay_tables(qa_model *M) {
                     }
                 const bool fits = E.size() + deg <= (size_t)RP_CAP && nbw + (int)row_words.size() <= RP_MAXBW;
                 if (!fits) {
-                    if (nv == 0) return QA_OK;   // a single row exceeds the format: dense model
+                    if (nv == 0) return false;   // a single row exceeds the format: dense model
                     break;
                 }
                 const int i = nv++;
                 const size_t start = E.size();
-                if (v < n && M->ngroups > 0 && hg[v] >= 0) {
-                    if (hc[v] >= (1 << 23) || hc[v] <= -(1 << 23)) return QA_OK;  // coefficient does not fit the packed form
+                if (v < n && ngroups > 0 && hg[v] >= 0) {
+                    if (hc[v] >= (1 << 23) || hc[v] <= -(1 << 23)) return false;  // coefficient does not fit the packed form
                     H.ga[i] = (int32_t)((uint32_t)hg[v] | ((uint32_t)hc[v] << 8));
                 }
                 H.nlater[i] = (uint16_t)later.size();
@@ -1623,7 +1617,7 @@ int build_replay_tables(qa_model *M) {
             H.v0 = v0;
             H.nv = nv;
             uniform = uniform && nv == RP_D;
-            if (slabs.size() / 16 > 0xfffffff0ull) return QA_OK;
+            if (slabs.size() / 16 > 0xfffffff0ull) return false;
             off.push_back((uint32_t)(slabs.size() / 16));
             hdr_pos.push_back(slabs.size());
             const unsigned char *hp = reinterpret_cast<const unsigned char *>(&H);
@@ -1633,7 +1627,7 @@ int build_replay_tables(qa_model *M) {
             v0 += nv;
         }
         nslabs[p] = b;
-        if ((int64_t)b * 4 > (int64_t)npad) return QA_OK;   // fewer than 4 variables per block on average: replaying does not pay
+        if ((int64_t)b * 4 > (int64_t)npad) return false;   // fewer than 4 variables per block on average: replaying does not pay
         // every slab also carries the word list of the next block (cyclic) for the L2 run-ahead of its {S,F} rows
         for (size_t k = 0; k < hdr_pos.size(); ++k) {
             RpHdr *cur = reinterpret_cast<RpHdr *>(slabs.data() + hdr_pos[k]);
@@ -1643,7 +1637,40 @@ int build_replay_tables(qa_model *M) {
         }
     }
     off.push_back((uint32_t)(slabs.size() / 16));
-    if (slabs.empty()) return QA_OK;
+    return !slabs.empty();
+}
+
+int build_replay_tables(qa_model *M) {
+    if (M->rp_built) return QA_OK;
+    qa_ctx *ctx = M->ctx;
+    M->rp_built = true;
+    M->rp_ok = false;
+    const int64_t entries = 2 * M->m_total;
+    const int64_t rows_alloc = M->n_total + 64 + 1;
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> rowptr(rows_alloc), col(std::max<int64_t>(entries, 1));
+    std::vector<double> val(std::max<int64_t>(entries, 1));
+    QA_CUDA(cudaMemcpy(rowptr.data(), M->rowptr, rows_alloc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (entries) {
+        QA_CUDA(cudaMemcpy(col.data(), M->col, entries * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        QA_CUDA(cudaMemcpy(val.data(), M->val, entries * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::vector<int32_t> hg, hc;
+    if (M->ngroups > 0) {
+        const int64_t npad = (int64_t)M->descs[0].nch * 32;
+        hg.resize(npad);
+        hc.resize(npad);
+        QA_CUDA(cudaMemcpy(hg.data(), M->grp, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        QA_CUDA(cudaMemcpy(hc.data(), M->coef, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    RpPacked pk;
+    if (!pack_replay_slabs(M->num_problems, M->var_off.data(), rowptr.data(), col.data(), val.data(), M->ngroups, hg, hc, pk))
+        return QA_OK;   // the model does not fit the slab format: rp_ok stays false
+    const std::vector<uint32_t> &off = pk.off;
+    const std::vector<unsigned char> &slabs = pk.slabs;
+    const std::vector<int64_t> &blk_base = pk.blk_base;
+    const std::vector<int32_t> &nslabs = pk.nslabs;
+    const bool uniform = pk.uniform;
     QA_CUDA(cudaMalloc((void **)&M->rp_slabs, slabs.size()));
     QA_CUDA(cudaMalloc((void **)&M->rp_off, off.size() * sizeof(uint32_t)));
     QA_CUDA(cudaMemcpyAsync(M->rp_slabs, slabs.data(), slabs.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1716,7 +1743,10 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
     // replay kernel (deferred exact updates): sparse models whose blocks fit the slab format; explicit choice, or automatic
     // from 6144 reads on (measured on B200, config 3: 1.26e10 vs 7.5e9 attempts/s for the warp-per-read kernel at 12 500
     // reads, 4.3e9 vs 5.9e9 at 4096)
-    if (mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ &&
+    // an interrupt callback is polled between read waves: only the warp-per-read kernel runs in waves, the lockstep and
+    // replay kernels anneal all reads in one launch
+    if (interrupt && mode == QA_MODE_REFERENCE) kernel = QA_KERNEL_WARP_PER_READ;
+    if (!interrupt && mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ &&
         (ctx->kernel == QA_KERNEL_REPLAY ||
          (ctx->kernel == QA_KERNEL_AUTO && (int64_t)reads_per_problem >= 32 && total_reads >= 6144))) {
         rc = build_replay_tables(M);
