@@ -22,8 +22,8 @@
 // the hand-over point does not influence the result.
 //
 // Coupling slabs: the host packs consecutive variables greedily into blocks (at most RP_D variables, RP_MAXBW foreign spin
-// words, RP_CAP entries, never across a 32-variable spin word) and builds one contiguous slab {RpHdr, RpEntry[]} per block (replay order,
-// 2J premultiplied, slot/bit of the neighbour's spin word).  All warps of a CTA walk the blocks together; slabs are brought
+// words, RP_CAP entries, never across a 32-variable spin word) and builds one contiguous slab {RpHdr, RpEntry[]} per block
+// (replay order, 2J premultiplied, slot/bit of the neighbour's spin word).  All warps of a CTA walk the blocks together; slabs are brought
 // into a 4-stage shared-memory ring with cp.async.bulk (TMA 1-D) completing on mbarriers, and released by one mbarrier arrive
 // per warp -- no __syncthreads in the sweep.  There is no fixed producer: whichever warp first gets within RP_DIST blocks of a
 // slab that has not been requested yet claims it (one shared-memory CAS) and issues the copy, so the ring runs at the pace
@@ -67,11 +67,12 @@ struct alignas(16) RpHdr {
     int32_t bw_next[RP_MAXBW];
 };
 static_assert(sizeof(RpHdr) % 16 == 0, "slab header layout");
-constexpr uint32_t RP_H_NBW = offsetof(RpHdr, nbw), RP_H_V0 = offsetof(RpHdr, v0), RP_H_NV = offsetof(RpHdr, nv), RP_H_ROW = offsetof(RpHdr, row), RP_H_NLATER = offsetof(RpHdr, nlater),
+constexpr uint32_t RP_H_NBW = offsetof(RpHdr, nbw), RP_H_V0 = offsetof(RpHdr, v0), RP_H_NV = offsetof(RpHdr, nv),
+                   RP_H_ROW = offsetof(RpHdr, row), RP_H_NLATER = offsetof(RpHdr, nlater),
                    RP_H_DEG = offsetof(RpHdr, deg), RP_H_GA = offsetof(RpHdr, ga), RP_H_BW = offsetof(RpHdr, bw),
                    RP_H_NBWN = offsetof(RpHdr, nbw_next), RP_H_BWN = offsetof(RpHdr, bw_next);
 struct __align__(16) RpEntry {
-    double J2;     // 2 * J (padding entries: 0)
+    double J2;     // 2 * J
     int32_t j;     // neighbour (local variable index)
     uint32_t B;    // bits 0-4: 31 - (j & 31); bits 8-12: slot; bit 15: neighbour inside the same block
 };
@@ -148,7 +149,7 @@ struct RpCtx {
     // per lane
     double *fT;                          // f[v][lane], this lane's column
     uint2 *SF;                           // {S,F}[word][lane], this lane's column
-    uint32_t sfbase_s;                   // shared address of this lane's column in the warp's 8 KB-aligned region
+    uint32_t sfbase_s;                   // shared address of this lane's column in the warp's size-aligned region
     int *Mcol;
     int mstride;
     const double *lam;

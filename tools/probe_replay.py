@@ -44,7 +44,6 @@ for sweeps in [int(x) for x in a.sweeps.split(",")]:
                 states = states0.copy()
                 e, st, done = gm.sample(states, betas, spb, seeds)
                 print(f"sweeps {len(betas)} permille {pm} warps {warps} kernel {ctx.last_kernel}: anneal_ms {st.ms_anneal:.1f} "
-                      f"attempts/s {st.attempts / st.ms_anneal * 1e3:.3e} acc {st.accepted / st.attempts:.4f} best {e.min() + model.offset:.3f} "
-                      f"ring-wait cycles/warp: slab {st.chunks / (a.reads / 32):.3e} stage {st.active_chunks / (a.reads / 32):.3e}",
+                      f"attempts/s {st.attempts / st.ms_anneal * 1e3:.3e} acc {st.accepted / st.attempts:.4f} best {e.min() + model.offset:.3f}",
                       flush=True)
                 gm.close()
