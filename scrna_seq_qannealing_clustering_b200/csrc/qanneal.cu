@@ -126,6 +126,7 @@ struct AnnealParams {
     int64_t groups_per_problem;  // ceil(tiles_per_problem / warps per CTA)
     int64_t total_items;         // num_problems * groups_per_problem
     int32_t switch_permille;     // replay -> push hand-over: CTA-wide acceptance of a sweep below this many per mille
+    int32_t rp_slab_init;        // adjacency lists ascending: the field set-up pass runs through the slab ring
 };
 
 enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
@@ -1265,6 +1266,7 @@ struct qa_model {
     uint32_t *rp_off = nullptr;
     bool rp_built = false, rp_ok = false;
     bool rp_uniform = false;   // every block holds exactly RP_D variables
+    bool rp_adj_sorted = false; // adjacency lists ascending: field set-up through the slab ring
     bool groups_i32 = false;   // every group term a*(a - s*(M+kappa)) fits 32-bit integers
 };
 
@@ -1511,6 +1513,7 @@ struct RpPacked {
     std::vector<int64_t> blk_base;      // first slab of every problem in `off`
     std::vector<int32_t> nslabs;
     bool uniform = true;                // every block holds exactly RP_D variables
+    bool adj_sorted = true;             // every adjacency list is ascending (dimod's vector order): slab order serves the set-up
 };
 
 bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, const int32_t *col, const double *val, int ngroups,
@@ -1525,6 +1528,7 @@ bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, con
     blk_base.assign(P, 0);
     nslabs.assign(P, 0);
     uniform = true;
+    out.adj_sorted = true;
     std::vector<int32_t> stamp, slot_of;
     std::vector<std::pair<int32_t, double>> later, earlier;
     std::vector<RpEntry> E;
@@ -1557,6 +1561,7 @@ bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, con
                     for (int64_t e = rowptr[v_off + v]; e < rowptr[v_off + v + 1]; ++e) {
                         if (col[e] > v) later.emplace_back(col[e], val[e]);
                         else earlier.emplace_back(col[e], val[e]);
+                        if (e > rowptr[v_off + v] && col[e] < col[e - 1]) out.adj_sorted = false;
                     }
                 }
                 auto by_index = [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b2) { return a.first < b2.first; };
@@ -1671,6 +1676,7 @@ int build_replay_tables(qa_model *M) {
     const std::vector<int64_t> &blk_base = pk.blk_base;
     const std::vector<int32_t> &nslabs = pk.nslabs;
     const bool uniform = pk.uniform;
+    M->rp_adj_sorted = pk.adj_sorted;
     QA_CUDA(cudaMalloc((void **)&M->rp_slabs, slabs.size()));
     QA_CUDA(cudaMalloc((void **)&M->rp_off, off.size() * sizeof(uint32_t)));
     QA_CUDA(cudaMemcpyAsync(M->rp_slabs, slabs.data(), slabs.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1873,6 +1879,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         A.total_items = total_items;
         A.max_groups = mg;
         A.switch_permille = ctx->replay_switch_permille;
+        A.rp_slab_init = M->rp_adj_sorted ? 1 : 0;
         A.read_begin = 0;
         A.read_end = total_reads;
         QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -154,6 +154,7 @@ struct RpCtx {
     int mstride;
     const double *lam;
     const long long *kap;
+    const double *h;                     // linear biases of the current problem (field set-up pass)
     unsigned long long s0, s1;
     LaneStats st;
     bool active;
@@ -193,7 +194,9 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
 }
 
 // One pass over all blocks.  MODE 0: replay sweep (pull).  MODE 1: catch-up (pending later-neighbour updates only, no
-// decisions).  MODE 2: push sweep (neal's eager form).  Returns the number of accepted flips of the warp.
+// decisions).  MODE 2: push sweep (neal's eager form).  MODE 3: field set-up f[v] = h_v + sum_j J_vj s_j in neal's
+// get_flip_energy order, for models whose adjacency lists are ascending (then adjacency order = the slab's earlier part
+// followed by its later part).  Returns the number of accepted flips of the warp.
 // GROUPS: 0 none, 1 rank-1 groups with 32-bit exact integer arithmetic (host-checked ranges), 2 with 64-bit.
 // VAR: blocks of variable size (read from the slab header); false = every block holds exactly RP_D variables, which lets the
 // compiler keep the block geometry in immediates (22 % faster on config 3: the kernel sits at the 128-register limit).
@@ -248,7 +251,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + k * 1024));
         }
-        if (MODE <= 1) {   // ... and of the {S,F} rows the next block will stage (8 sectors per word)
+        if (MODE <= 1 || MODE == 3) {   // ... and of the {S,F} rows the next block will stage (8 sectors per word)
             const int ns = (int)lds_u32(hdr + RP_H_NBWN) * 8;
             const char *sfrow = reinterpret_cast<const char *>(SF - lane);
             for (int k = lane; k < ns; k += 32) {
@@ -259,7 +262,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
         }
 #endif
         bool blk_dirty = false;
-        if (MODE <= 1) {
+        if (MODE <= 1 || MODE == 3) {
             // this lane's copy of every spin/flag word the block refers to (~S so that a set top bit means "spin down")
             const int nbw = (int)lds_u32(hdr + RP_H_NBW);
             for (int s = 0; s < nbw; s += 8) {
@@ -300,7 +303,37 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
             const uint32_t bit = 1u << (sub + i);
             const bool up = (S & bit) != 0u;
             double fv;
-            if (MODE <= 1) {
+            if (MODE == 3) {
+                // h_v, then the earlier neighbours (ascending), then the later ones: 0.5 * (+-2J) is exact, one rounding per term
+                fv = __ldg(c.h + v0 + i);
+                const uint32_t am = a0 + (lds_u16(hdr + RP_H_NLATER + 2u * (uint32_t)i) & 0xfffu) * 16u;
+                const uint32_t a1 = ent + (rw >> 16) * 16u;
+                auto add1 = [&](const int4 &q, const uint2 &sf) {
+                    const uint32_t sg = __funnelshift_l(0u, sf.x, (uint32_t)q.w) & 0x80000000u;   // spin down: -J
+                    fv = fma(__hiloint2double(q.y ^ (int)sg, q.x), 0.5, fv);
+                };
+#pragma unroll
+                for (int seg = 0; seg < 2; ++seg) {
+                    uint32_t a = seg == 0 ? am : a0;
+                    const uint32_t ae = seg == 0 ? a1 : am;
+                    for (; a + 64u <= ae; a += 64u) {
+                        int4 q[4];
+                        uint2 sf[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) q[k] = lds_v4(a + 16u * k);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sf[k] = lds_u2(((uint32_t)q[k].w & RP_SLOT_MASK) | sfb);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) add1(q[k], sf[k]);
+                    }
+                    for (; a < ae; a += 16u) {
+                        const int4 q = lds_v4(a);
+                        add1(q, lds_u2(((uint32_t)q.w & RP_SLOT_MASK) | sfb));
+                    }
+                }
+                __stcg(fB + i * 32, fv);
+                continue;
+            } else if (MODE <= 1) {
                 fv = fq[0];
 #pragma unroll
                 for (int k = 0; k + 1 < RP_LA; ++k) fq[k] = fq[k + 1];
@@ -430,7 +463,7 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                     if (i < nv) __stcg(fB + i * 32, lds_f64(sfb + (uint32_t)i * 256u));
             }
         }
-        if (MODE != 1 && sub + nv == 32) {
+        if (MODE != 1 && MODE != 3 && sub + nv == 32) {
             if (S != S0 || F != F0) __stcg(SF + (int64_t)wi * 32, make_uint2(S, F));
         }
         // release the stage: one arrive per warp
@@ -442,6 +475,14 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
     c.t_pass += (unsigned long long)(clock64() - tp0);
 #endif
     return sweep_acc;
+}
+
+// The set-up pass as a real call with the context passed BY VALUE: its registers do not add to the pressure of the sweep
+// loops (the kernel sits at the 128-register limit and every spilled value there costs measurable time).
+template <bool VAR>
+__device__ __noinline__ uint32_t rp_setup_pass(RpCtx c) {
+    rp_pass<3, 0, VAR>(c, 1.0, true);
+    return c.gb;
 }
 
 // local field of v in neal's get_flip_energy order (adjacency order), spins from the {S,F} scratch; loads batched by 8
@@ -570,6 +611,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
         c.nblk = D.rp_nslabs;
         c.npad = D.nch * 32;
         c.slabs = D.rp_slabs;
+        c.h = D.h;
         c.off = D.rp_off;
         const long long total_sweeps = (long long)P.num_betas * P.sweeps_per_beta;
         if (lane == 0 && total_sweeps > 0) rp_request(c, c.gb + (uint32_t)RP_DIST, 0);   // overlaps with the set-up below
@@ -609,8 +651,11 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                 }
             }
         }
-        // ---- local fields in neal's get_flip_energy order
-        {
+        // ---- local fields in neal's get_flip_energy order: through the slab ring when the adjacency lists are ascending,
+        // else row by row from the CSR
+        if (P.rp_slab_init) {
+            if (total_sweeps > 0) c.gb = rp_setup_pass<VAR>(c);
+        } else {
             int e0 = __ldg(D.rowptr);
             for (int v = 0; v < n; ++v) {
                 const int e1 = __ldg(D.rowptr + v + 1);
