@@ -221,3 +221,40 @@ def test_python_replay_of_the_packed_slabs_equals_the_oracle(case):
     for r in range(R):
         out = replay_from_slabs(model, rows, blocks, init[r], betas, spb, int(seeds[r]))
         assert np.array_equal(out, ref[r]), r
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_graphs_invariants_and_replay(seed):
+    """Random sparse models (ragged sizes, shuffled / duplicated couplers, isolated variables, zero weights): the packed slabs
+    satisfy the block invariants and the Python replay driven by them reproduces the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 140))
+    m = int(min(n * (n - 1) // 2, rng.integers(0, 4 * n + 1)))
+    pairs = set()
+    while len(pairs) < m:
+        u, v = rng.integers(0, n, 2)
+        if u != v:
+            pairs.add((int(max(u, v)), int(min(u, v))))
+    pairs = sorted(pairs)
+    if pairs and seed % 2:
+        pairs += [pairs[i] for i in rng.integers(0, len(pairs), size=min(5, len(pairs)))]   # duplicated couplers
+        rng.shuffle(pairs)
+    flip = rng.random(len(pairs)) < 0.5
+    starts = np.array([p[1] if f else p[0] for p, f in zip(pairs, flip)], dtype=np.int32)
+    ends = np.array([p[0] if f else p[1] for p, f in zip(pairs, flip)], dtype=np.int32)
+    w = rng.normal(size=len(pairs)) / 2
+    if len(w):
+        w[rng.integers(0, len(w))] = 0.0
+    model = models.LoweredModel(rng.normal(size=n) / 3, starts, ends, w, 0.0, list(range(n)))
+    packed = pack(model)
+    if packed is None:
+        pytest.skip("model does not fit the slab format (fewer than 4 variables per block)")
+    rows, blocks, _ = packed
+    check_invariants(model, rows, blocks)
+    betas, spb = schedule.make_beta_schedule((0.05, 6.0), 12, 2, "geometric")
+    seeds = schedule.per_read_seeds(seed, 2)
+    init = schedule.random_spin_states(2, n, seed)
+    ref = init.copy()
+    oracle.sample_ising(model.h, model.starts, model.ends, model.weights, ref, betas, spb, seeds)
+    for r in range(2):
+        assert np.array_equal(replay_from_slabs(model, rows, blocks, init[r], betas, spb, int(seeds[r])), ref[r])
