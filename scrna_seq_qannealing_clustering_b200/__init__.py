@@ -10,7 +10,8 @@ from .dqm import DiscreteQuadraticModel
 from .sampleset import SampleSet
 from .sampler import B200SimulatedAnnealingSampler
 from .clustering import (clustering_bqm, clustering_bqm_2, clustering_bqm_3, clustering_cqm, clustering_cqm_2,
-                         clustering_dqm, graph_subsampling, disconnected_components)
+                         clustering_dqm, graph_subsampling, disconnected_components, recursive_bipartition_batched)
+from .graph_io import create_graph, create_graph_csv
 
 # the name a neal user would look for
 SimulatedAnnealingSampler = B200SimulatedAnnealingSampler
@@ -19,5 +20,5 @@ __all__ = [
     "BINARY", "SPIN", "Vartype", "BinaryQuadraticModel", "DiscreteQuadraticModel", "ConstrainedQuadraticModel", "Binary",
     "SampleSet", "B200SimulatedAnnealingSampler", "SimulatedAnnealingSampler", "clustering_bqm", "clustering_bqm_2",
     "clustering_bqm_3", "clustering_dqm", "clustering_cqm", "clustering_cqm_2", "graph_subsampling",
-    "disconnected_components",
+    "disconnected_components", "recursive_bipartition_batched", "create_graph", "create_graph_csv",
 ]
