@@ -56,6 +56,39 @@ def default_ising_beta_range(h: np.ndarray, irow: np.ndarray, icol: np.ndarray, 
     return float(np.log(2) / max_delta), float(np.log(100) / min_delta)
 
 
+def default_ising_beta_range_samplers(h: np.ndarray, irow: np.ndarray, icol: np.ndarray, qdata: np.ndarray,
+                                      max_single_qubit_excitation_rate: float = 0.01, scale_T_with_N: bool = True) -> Tuple[float, float]:
+    """The default range of dwave-samplers >= 1.0 (the package behind ``neal`` from Ocean 6 on; SURVEY.md row a12, restated
+    from the upstream description -- unpinned like the rest of the third-party behaviour):
+
+        hot  = ln 2 / (2 * max_v (|h_v| + sum_j |J_vj|))           (1 when the model has no bias at all)
+        cold = ln(N_min / rate) / (2 * f_min),   f_min = min_v (smallest non-zero |bias| touching v),
+               N_min = number of variables attaining f_min (1 when ``scale_T_with_N`` is false), rate = 0.01
+
+    ``default_ising_beta_range`` above is the dwave-neal 0.5.x rule, which the sampler uses unless a range is passed."""
+    h = np.asarray(h, dtype=np.float64)
+    q = np.asarray(qdata, dtype=np.float64)
+    n = len(h)
+    abs_h = np.abs(h)
+    field = abs_h.copy()
+    fmin = np.where(abs_h != 0, abs_h, np.inf)
+    if len(q):
+        aq = np.abs(q)
+        np.add.at(field, irow, aq)
+        np.add.at(field, icol, aq)
+        nzq = aq != 0
+        np.minimum.at(fmin, np.asarray(irow)[nzq], aq[nzq])
+        np.minimum.at(fmin, np.asarray(icol)[nzq], aq[nzq])
+    max_field = float(field.max()) if n else 0.0
+    hot = 1.0 if max_field == 0 else float(np.log(2) / (2 * max_field))
+    finite = fmin[np.isfinite(fmin)]
+    if len(finite) == 0:
+        return hot, hot
+    f = float(finite.min())
+    n_min = int(np.sum(finite == f)) if scale_T_with_N else 1
+    return hot, float(np.log(n_min / max_single_qubit_excitation_rate) / (2 * f))
+
+
 def make_beta_schedule(beta_range: Optional[Sequence[float]], num_sweeps: int, num_sweeps_per_beta: int,
                        beta_schedule_type: str, beta_schedule: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, int]:
     """Returns (beta_schedule, num_sweeps_per_beta) with neal's validation rules."""

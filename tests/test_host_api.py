@@ -206,3 +206,18 @@ def test_sampler_surface():
         warnings.simplefilter("always")
         s.sample(BinaryQuadraticModel({}, {}, 0.0, "SPIN"), label="x", chain_strength=4)
     assert len(w) == 2
+
+
+def test_dwave_samplers_default_beta_range_rule():
+    """The newer default range (dwave-samplers >= 1.0) on a hand-computable model: h = (1, 0, -2), J01 = 0.5, J12 = -0.25."""
+    h = np.array([1.0, 0.0, -2.0])
+    irow = np.array([1, 2], dtype=np.int32)
+    icol = np.array([0, 1], dtype=np.int32)
+    q = np.array([0.5, -0.25])
+    hot, cold = schedule.default_ising_beta_range_samplers(h, irow, icol, q)
+    # fields: v0 1.5, v1 0.75, v2 2.25 -> hot = ln2 / 4.5 ; smallest non-zero bias per variable: 0.5, 0.25, 0.25 -> two minima
+    assert hot == pytest.approx(np.log(2) / 4.5)
+    assert cold == pytest.approx(np.log(2 / 0.01) / 0.5)
+    _, cold1 = schedule.default_ising_beta_range_samplers(h, irow, icol, q, scale_T_with_N=False)
+    assert cold1 == pytest.approx(np.log(1 / 0.01) / 0.5)
+    assert schedule.default_ising_beta_range_samplers(np.zeros(3), np.zeros(0, int), np.zeros(0, int), np.zeros(0)) == (1.0, 1.0)
