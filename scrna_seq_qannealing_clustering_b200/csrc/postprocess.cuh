@@ -168,7 +168,7 @@ int qa_debug_pack_slabs(int32_t n, const int32_t *rowptr, const int32_t *col, co
                         const int32_t *grp, const int32_t *coef, int64_t *nslabs_out, int64_t *bytes_out, int32_t *uniform_out,
                         unsigned char *slabs_out, uint32_t *off_out) {
     if (n < 1 || !rowptr || !nslabs_out || !bytes_out || !uniform_out) return fail(QA_ERR_ARG, "bad arguments");
-    const int64_t npad = ((int64_t)n + 31) / 32 * 32;
+    const int64_t npad = ((int64_t)n + 31) / 32 * 32;   // covers the packer's 16-variable padding
     std::vector<int32_t> rp(npad + 1);
     for (int64_t v = 0; v <= npad; ++v) rp[v] = rowptr[std::min<int64_t>(v, n)];
     std::vector<int32_t> hg, hc;

@@ -32,6 +32,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -121,12 +122,13 @@ struct AnnealParams {
     int32_t max_groups;          // stride of the per-thread group counters in shared memory
     int64_t total_tiles;
     // replay kernel (one CTA = `warps` consecutive 32-read tiles of one problem)
-    void *sf_scratch;            // [slots][sf_stride] {S,F} words, read-interleaved (uint2)
-    int64_t sf_stride;           // nch_max * 32
+    void *sf_scratch;            // [slots][sf_stride] {S | F << 16} half-word words, read-interleaved (uint32)
+    int64_t sf_stride;           // nch_max * 2 * 32
     int64_t groups_per_problem;  // ceil(tiles_per_problem / warps per CTA)
     int64_t total_items;         // num_problems * groups_per_problem
     int32_t switch_permille;     // replay -> push hand-over: CTA-wide acceptance of a sweep below this many per mille
     int32_t rp_slab_init;        // adjacency lists ascending: the field set-up pass runs through the slab ring
+    const int *interrupt_flag;   // host-mapped flag (or null): CTAs stop pulling work once it is non-zero
 };
 
 enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
@@ -462,32 +464,36 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // accept test of one variable for every lane (read) of the warp; returns the per-lane accept flag.
-// neal: flip iff exp(-dE*beta) * 2^64 > (double)rand.  Evaluating the fp64 exp for every draw is the longest dependent chain
-// of a step, so the draw is first screened against a single-precision estimate: pa = ex2.approx(float(x) * log2 e) is
-// within 1e-5 relative of exp(x) for x in [-44.4, 0] (conversion 9e-8 of x <= 44, i.e. 4e-6 in the exponent, plus 2 ulp
-// of ex2.approx), so a draw outside [pa * (1 - 1e-4), pa * (1 + 1e-4)] * 2^64 is decided exactly as the fp64 comparison
-// would decide it.  Only draws inside that band (2e-4 of them) take the fp64 path -- the result is identical by construction,
+// neal: flip iff exp(-dE*beta) * 2^64 > (double)rand.  The fp64 exp, the 64-bit conversion and the fp64 products are the
+// longest dependent chain of a step, so the draw is first screened in SINGLE precision on its upper 32 bits:
+//   pa = ex2.approx(float(dE) * float(-beta * log2 e)) is within 3e-5 relative of exp(-dE*beta) for -dE*beta in [-44.4, 0]
+//        (two roundings of 6e-8 on an exponent of magnitude <= 64 -> 1.2e-5 absolute in the exponent -> 8e-6, + 2 ulp of
+//        ex2.approx);
+//   rh = float(rand >> 32): rand / 2^32 lies in [rh', rh' + 1) with rh' = floor(rand / 2^32), |rh - rh'| <= 6e-8 rh'.
+// rh + 1 < 0.9999 * pa * 2^32  =>  rand < 0.99994 * exp(..) * 2^64: every fp64 evaluation accepts;
+// rh     > 1.0001 * pa * 2^32  =>  rand > 1.00006 * exp(..) * 2^64: every fp64 evaluation rejects.
+// Only draws inside that band (2e-4 of them, + 2^-32 / p) take the fp64 path -- the result is identical by construction,
 // and near ties (|p - r| <= 2^-48 p) can only occur inside the band, where they are still counted.
 __device__ __forceinline__ bool ls_accept(double dE, bool cand, double beta, unsigned long long &s0, unsigned long long &s1,
                                           LaneStats &st) {
     bool acc = cand;
     const bool need = cand && dE > 0.0;
     bool exact = false;
-    double x = 0.0, rd = 0.0;
+    unsigned long long rnd = 0ull;
     if (need) {
-        const unsigned long long rnd = rng_next(s0, s1);
+        rnd = rng_next(s0, s1);
         st.draws++;
-        x = -dE * beta;
-        rd = __ull2double_rn(rnd);
         float pa;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pa) : "f"(__double2float_rn(x) * 1.44269504088896341f));
-        const double pd = (double)pa * QA_TWO64;
-        acc = rd < pd * 0.9999;
-        exact = !acc && !(rd > pd * 1.0001);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pa) : "f"(__double2float_rn(dE) * __double2float_rn(beta * -1.4426950408889634)));
+        const float rh = __uint2float_rn((unsigned)(rnd >> 32));
+        acc = rh + 1.0f < pa * 4294537799.0f;               // 0.9999 * 2^32
+        exact = !acc && !(rh > pa * 4295396793.0f);         // 1.0001 * 2^32
     }
     if (__any_sync(FULL_MASK, exact)) {
         if (exact) {
-            const double p = exp(x) * QA_TWO64;
+            const double p = exp(-dE * beta) * QA_TWO64;
+            double rd;   // volatile: the conversion must stay inside this rare path (the compiler would hoist it)
+            asm volatile("cvt.rn.f64.u64 %0, %1;" : "=d"(rd) : "l"(rnd));
             acc = p > rd;
             if (fabs(p - rd) <= p * 3.5527136788005009e-15) st.ties++;
         }
@@ -1230,6 +1236,7 @@ struct qa_ctx {
     int last_kernel = 0;              // QA_KERNEL_* the last sampling call ran on
     unsigned rp_smem_base = 1024;     // shared-window offset of dynamic shared memory (verified by the replay kernel)
     bool rp_base_checked = false;
+    int *h_iflag = nullptr, *d_iflag = nullptr;  // host-mapped interrupt flag polled by the replay kernel
     unsigned long long *d_stats = nullptr;  // QA_NSTAT counters + 1 read counter
     int *d_flag = nullptr;
     double *d_best_e = nullptr;
@@ -1498,13 +1505,14 @@ int build_word_tables(qa_model *M) {
     return QA_OK;
 }
 
-// Coupling slabs of the replay kernel (replay.cuh): per block of RP_D variables one contiguous {RpHdr, RpEntry[]} record
-// with the rows in REPLAY order -- neighbours u > v ascending, then u < v ascending (stable, so duplicate couplers keep their
-// adjacency order) -- 2J premultiplied, and the slot / bit of the neighbour's spin word.  Built once per model on the host
-// from the device-built CSR (a setup step, O(entries)).  Consecutive variables are packed greedily into blocks of at most RP_D
-// variables, RP_CAP entries and RP_MAXBW foreign spin words, never across a 32-variable spin word.  Models whose blocks would
-// hold fewer than 4 variables on average (dense rows, or sparse rows scattered over many words) leave rp_ok false and run on
-// the other kernels.
+// Coupling slabs of the replay kernel (replay.cuh): per block one contiguous {RpHdr, RpEntry[]} record.  Consecutive variables are packed greedily into blocks of at most RP_D variables inside
+// ONE 16-variable half-word, RP_MAXBW foreign half-words and RP_CAP entry slots.  A row's entries are in REPLAY order --
+// neighbours u > v ascending, then u < v ascending (stable, so duplicate couplers keep their adjacency order) -- split
+// into the PRE part (u > v, then u < v0: known when the block starts; padded to rounds of 4 with
+// zero-coupling entries) and the SEQ part (v0 <= u < v: decided inside the block).  The slab holds the pre parts of all
+// rows, then the seq parts of all rows.  Built once per model on the host from the device-built CSR (a setup step,
+// O(entries)).  Models whose blocks would hold fewer than 4 variables on average (dense rows, or sparse rows scattered over
+// many half-words) leave rp_ok false and run on the other kernels.
 // Pure host part of the slab construction (no CUDA calls: the CPU test-suite drives it through qa_debug_pack_slabs).
 // rowptr holds global entry positions per global row (problem p's rows start at var_off[p]), col local neighbour indices.
 struct RpPacked {
@@ -1520,108 +1528,118 @@ bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, con
                        const std::vector<int32_t> &hg, const std::vector<int32_t> &hc, RpPacked &out) {
     std::vector<uint32_t> &off = out.off;
     std::vector<unsigned char> &slabs = out.slabs;
-    std::vector<int64_t> &blk_base = out.blk_base;
-    std::vector<int32_t> &nslabs = out.nslabs;
-    bool &uniform = out.uniform;
+    out.blk_base.assign(P, 0);
+    out.nslabs.assign(P, 0);
     off.clear();
     slabs.clear();
-    blk_base.assign(P, 0);
-    nslabs.assign(P, 0);
-    uniform = true;
+    out.uniform = true;
     out.adj_sorted = true;
+    struct Nb { int32_t j; double J; };
+    struct Row { std::vector<Nb> later, early, seq; };   // u > v | u < v0 | v0 <= u < v
     std::vector<int32_t> stamp, slot_of;
-    std::vector<std::pair<int32_t, double>> later, earlier;
-    std::vector<RpEntry> E;
+    std::vector<Row> rows(RP_D);
     std::vector<size_t> hdr_pos;
     std::vector<int32_t> row_words;
     for (int p = 0; p < P; ++p) {
         const int64_t v_off = var_off[p];
         const int n = (int)(var_off[p + 1] - v_off);
-        if (n == 0) return false;
-        const int nch = (n + 31) / 32;
-        const int npad = nch * 32;
-        blk_base[p] = (int64_t)off.size();
+        if (n == 0 || n > RP_MAX_VARS) return false;   // the entry word holds a 20-bit neighbour index
+        const int nhw = (n + 15) / 16;
+        const int npad = nhw * 16;
+        out.blk_base[p] = (int64_t)off.size();
         hdr_pos.clear();
-        stamp.assign(nch, -1);
-        slot_of.assign(nch, 0);
-        int b = 0;   // block (slab) index inside the problem; doubles as the stamp of the word -> slot map
+        stamp.assign(nhw, -1);
+        slot_of.assign(nhw, 0);
+        int b = 0;   // block (slab) index inside the problem; doubles as the stamp of the half-word -> slot map
         for (int v0 = 0; v0 < npad; ++b) {
-            const int own = v0 >> 5;
-            const int vmax = std::min({v0 + RP_D, (own + 1) * 32});   // never across a spin word
+            const int own = v0 >> 4;
+            const int vmax = std::min(v0 + RP_D, (own + 1) * 16);   // never across a half-word
             RpHdr H;
             memset(&H, 0, sizeof(H));
             for (int i = 0; i < RP_D; ++i) H.ga[i] = 255;
-            E.clear();
             int nbw = 0, nv = 0;
+            size_t slots_pre = 0, slots_seq = 0;
             for (int v = v0; v < vmax; ++v) {
-                // the row of v in replay order
-                later.clear();
-                earlier.clear();
+                Row &R = rows[nv];
+                R.later.clear();
+                R.early.clear();
+                R.seq.clear();
                 if (v < n) {
                     for (int64_t e = rowptr[v_off + v]; e < rowptr[v_off + v + 1]; ++e) {
-                        if (col[e] > v) later.emplace_back(col[e], val[e]);
-                        else earlier.emplace_back(col[e], val[e]);
+                        const Nb nb{col[e], val[e]};
+                        if (nb.j > v) R.later.push_back(nb);
+                        else if (nb.j < v0) R.early.push_back(nb);
+                        else R.seq.push_back(nb);
                         if (e > rowptr[v_off + v] && col[e] < col[e - 1]) out.adj_sorted = false;
                     }
                 }
-                auto by_index = [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b2) { return a.first < b2.first; };
-                std::stable_sort(later.begin(), later.end(), by_index);
-                std::stable_sort(earlier.begin(), earlier.end(), by_index);
-                const size_t deg = later.size() + earlier.size();
-                // does the row still fit into this block?  (entries, and the foreign spin words it would add)
+                auto by_index = [](const Nb &a, const Nb &b2) { return a.j < b2.j; };
+                std::stable_sort(R.later.begin(), R.later.end(), by_index);
+                std::stable_sort(R.early.begin(), R.early.end(), by_index);
+                std::stable_sort(R.seq.begin(), R.seq.end(), by_index);
+                const size_t npre = R.later.size() + R.early.size();
+                const size_t deg = npre + R.seq.size();
+                if (R.seq.size() > 255 || deg > 0xffff) return false;
+                // does the row still fit into this block?  (entry slots, and the foreign half-words it would add)
                 row_words.clear();
                 for (int part = 0; part < 2; ++part)
-                    for (const auto &nb : (part == 0 ? later : earlier)) {
-                        const int wj = nb.first >> 5;
+                    for (const Nb &nb : (part == 0 ? R.later : R.early)) {
+                        const int wj = nb.j >> 4;
                         if (wj != own && stamp[wj] != b && std::find(row_words.begin(), row_words.end(), wj) == row_words.end())
                             row_words.push_back(wj);
                     }
-                const bool fits = E.size() + deg <= (size_t)RP_CAP && nbw + (int)row_words.size() <= RP_MAXBW;
+                const size_t pre_slots = (npre + 3) / 4 * 4;
+                const bool fits = slots_pre + slots_seq + pre_slots + R.seq.size() <= (size_t)RP_CAP &&
+                                  nbw + (int)row_words.size() <= RP_MAXBW && pre_slots / 4 <= 255;
                 if (!fits) {
                     if (nv == 0) return false;   // a single row exceeds the format: dense model
                     break;
                 }
+                for (int wj : row_words) {
+                    stamp[wj] = b;
+                    slot_of[wj] = nbw + 1;
+                    H.bw[nbw++] = wj;
+                }
                 const int i = nv++;
-                const size_t start = E.size();
                 if (v < n && ngroups > 0 && hg[v] >= 0) {
                     if (hc[v] >= (1 << 23) || hc[v] <= -(1 << 23)) return false;  // coefficient does not fit the packed form
                     H.ga[i] = (int32_t)((uint32_t)hg[v] | ((uint32_t)hc[v] << 8));
                 }
-                H.nlater[i] = (uint16_t)later.size();
-                H.deg[i] = (uint16_t)deg;
-                for (int part = 0; part < 2; ++part) {
-                    for (const auto &nb : (part == 0 ? later : earlier)) {
-                        const int j = nb.first;
-                        const int wj = j >> 5;
-                        int slot = 0;
-                        if (wj != own) {
-                            if (stamp[wj] != b) {
-                                stamp[wj] = b;
-                                slot_of[wj] = nbw + 1;
-                                H.bw[nbw++] = wj;
-                            }
-                            slot = slot_of[wj];
-                        }
-                        RpEntry en;
-                        en.J2 = 2.0 * nb.second;
-                        en.j = j;
-                        en.B = (uint32_t)(31 - (j & 31)) | ((uint32_t)slot << 8) | ((j >= v0 && j < vmax) ? 0x4000u : 0u);
-                        E.push_back(en);
-                    }
+                H.rowa[i] = (uint32_t)(pre_slots / 4) | ((uint32_t)R.seq.size() << 8) | ((uint32_t)deg << 16);
+                H.rowb[i] = (uint32_t)R.later.size() | ((uint32_t)npre << 16);
+                slots_pre += pre_slots;
+                slots_seq += R.seq.size();
+            }
+            // the block is closed: lay out the pre region (rows in order, padded), then the seq region
+            std::vector<RpEntry> E;
+            E.reserve(slots_pre + slots_seq);
+            auto emit = [&](const Nb &nb) {
+                const int wj = nb.j >> 4;
+                RpEntry en;
+                en.J = nb.J;
+                en.zero = 0u;
+                en.B = (uint32_t)(30 - 2 * (nb.j & 15)) | ((uint32_t)(wj == own ? 0 : slot_of[wj]) << 7) | ((uint32_t)nb.j << 12);
+                E.push_back(en);
+            };
+            for (int i = 0; i < nv; ++i) {
+                for (const Nb &nb : rows[i].later) emit(nb);
+                for (const Nb &nb : rows[i].early) emit(nb);
+                while (E.size() % 4) {
+                    RpEntry en;
+                    en.J = 0.0;          // fma(0, sigma, f) == f
+                    en.zero = 0u;
+                    en.B = 30u | ((uint32_t)(v0 + i) << 12);   // slot 0
+                    E.push_back(en);
                 }
-                H.row[i] = (uint32_t)start | ((uint32_t)(start + deg) << 16);
             }
-            // "neighbour inside the same block" is known only now that the block is closed
-            for (auto &en : E) {
-                const bool near = (en.B & 0x4000u) && en.j < v0 + nv;
-                en.B = (en.B & ~0xC000u) | (near ? 0x8000u : 0u);
-            }
-            for (int i = nv; i < RP_D; ++i) H.row[i] = (uint32_t)E.size() | ((uint32_t)E.size() << 16);
+            H.seq_off = (int32_t)E.size();
+            for (int i = 0; i < nv; ++i)
+                for (const Nb &nb : rows[i].seq) emit(nb);
             H.nent = (int32_t)E.size();
             H.nbw = nbw;
             H.v0 = v0;
             H.nv = nv;
-            uniform = uniform && nv == RP_D;
+            out.uniform = out.uniform && nv == RP_D;
             if (slabs.size() / 16 > 0xfffffff0ull) return false;
             off.push_back((uint32_t)(slabs.size() / 16));
             hdr_pos.push_back(slabs.size());
@@ -1631,14 +1649,23 @@ bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, con
             slabs.insert(slabs.end(), ep, ep + E.size() * sizeof(RpEntry));
             v0 += nv;
         }
-        nslabs[p] = b;
+        out.nslabs[p] = b;
         if ((int64_t)b * 4 > (int64_t)npad) return false;   // fewer than 4 variables per block on average: replaying does not pay
-        // every slab also carries the word list of the next block (cyclic) for the L2 run-ahead of its {S,F} rows
+        // every slab also carries the half-word list of the next block (cyclic), staged while this block decides, and the slot
+        // that holds the PREVIOUS block's half-word (the one word that staging cannot have up to date)
         for (size_t k = 0; k < hdr_pos.size(); ++k) {
             RpHdr *cur = reinterpret_cast<RpHdr *>(slabs.data() + hdr_pos[k]);
             const RpHdr *nxt = reinterpret_cast<const RpHdr *>(slabs.data() + hdr_pos[(k + 1) % hdr_pos.size()]);
             cur->nbw_next = nxt->nbw;
             memcpy(cur->bw_next, nxt->bw, sizeof(cur->bw_next));
+            cur->prev_slot = 0;
+            if (k > 0) {
+                const RpHdr *prv = reinterpret_cast<const RpHdr *>(slabs.data() + hdr_pos[k - 1]);
+                const int phw = prv->v0 >> 4;
+                if (phw != (cur->v0 >> 4))
+                    for (int s = 0; s < cur->nbw; ++s)
+                        if (cur->bw[s] == phw) cur->prev_slot = s + 1;
+            }
         }
     }
     off.push_back((uint32_t)(slabs.size() / 16));
@@ -1749,10 +1776,10 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
     // replay kernel (deferred exact updates): sparse models whose blocks fit the slab format; explicit choice, or automatic
     // from 6144 reads on (measured on B200, config 3: 1.26e10 vs 7.5e9 attempts/s for the warp-per-read kernel at 12 500
     // reads, 4.3e9 vs 5.9e9 at 4096)
-    // an interrupt callback is polled between read waves: only the warp-per-read kernel runs in waves, the lockstep and
-    // replay kernels anneal all reads in one launch
-    if (interrupt && mode == QA_MODE_REFERENCE) kernel = QA_KERNEL_WARP_PER_READ;
-    if (!interrupt && mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ &&
+    // an interrupt callback: the warp-per-read kernel runs in read waves and polls between them; the replay kernel polls a
+    // host-mapped flag whenever a CTA pulls its next group of reads; the lockstep push kernel has no stopping point
+    if (interrupt && kernel == QA_KERNEL_LOCKSTEP_PUSH) kernel = QA_KERNEL_WARP_PER_READ;
+    if (mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ && (!interrupt || P == 1) &&
         (ctx->kernel == QA_KERNEL_REPLAY ||
          (ctx->kernel == QA_KERNEL_AUTO && (int64_t)reads_per_problem >= 32 && total_reads >= 6144))) {
         rc = build_replay_tables(M);
@@ -1761,7 +1788,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
             kernel = QA_KERNEL_REPLAY;
             QA_CUDA(cudaMemcpyAsync(M->d_descs, M->descs.data(), P * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
         } else if (ctx->kernel == QA_KERNEL_REPLAY) {
-            kernel = QA_KERNEL_LOCKSTEP_PUSH;  // dense model: the slab format does not apply
+            kernel = interrupt ? QA_KERNEL_WARP_PER_READ : QA_KERNEL_LOCKSTEP_PUSH;  // dense model: the slab format does not apply
         }
     }
 
@@ -1844,30 +1871,25 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         const int64_t gpp = (tpp + nw - 1) / nw;
         const int64_t total_items = (int64_t)P * gpp;
         size_t smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
-        const void *fn = nullptr;
-        if (M->rp_uniform)
-            fn = !groups ? (const void *)k_anneal_replay<0, false>
-                         : (M->groups_i32 ? (const void *)k_anneal_replay<1, false> : (const void *)k_anneal_replay<2, false>);
-        else
-            fn = !groups ? (const void *)k_anneal_replay<0, true>
-                         : (M->groups_i32 ? (const void *)k_anneal_replay<1, true> : (const void *)k_anneal_replay<2, true>);
+        const void *fn = !groups ? (const void *)k_anneal_replay<0>
+                                 : (M->groups_i32 ? (const void *)k_anneal_replay<1> : (const void *)k_anneal_replay<2>);
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
         QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, nw * 32, smem, cudaOccupancyDefault));
         if (bps < 1) return fail(QA_ERR_CUDA, "replay kernel does not fit on an SM");
         int64_t grid = std::min<int64_t>((int64_t)bps * ctx->num_sms, total_items);
         const int64_t fT_stride = (int64_t)M->nch_max * 32 * 32;
-        const int64_t sf_stride = (int64_t)M->nch_max * 32;
+        const int64_t sf_stride = (int64_t)M->nch_max * 2 * 32;
         {
             size_t free_b = 0, total_b = 0;
             QA_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const size_t per_slot = (size_t)fT_stride * sizeof(double) + (size_t)sf_stride * sizeof(uint2);
+            const size_t per_slot = (size_t)fT_stride * sizeof(double) + (size_t)sf_stride * sizeof(uint32_t);
             const size_t budget = (size_t)((double)(free_b + ctx->fT.bytes + ctx->sf.bytes) * 0.9);
             const int64_t max_slots = (int64_t)(budget / per_slot);
             if (max_slots < nw) return fail(QA_ERR_CUDA, "not enough device memory for one CTA of local fields");
             if (grid * nw > max_slots) grid = max_slots / nw;
-            rc = ensure(ctx->fT, (size_t)grid * nw * fT_stride * sizeof(double));
-            if (!rc) rc = ensure(ctx->sf, (size_t)grid * nw * sf_stride * sizeof(uint2));
+            rc = ensure(ctx->fT, (size_t)grid * nw * fT_stride * sizeof(double) + 4096);   // + the look-ahead rows of the last slot
+            if (!rc) rc = ensure(ctx->sf, (size_t)grid * nw * sf_stride * sizeof(uint32_t));
             if (rc) return rc;
         }
         A.fT_scratch = (double *)ctx->fT.p;
@@ -1882,6 +1904,10 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         A.rp_slab_init = M->rp_adj_sorted ? 1 : 0;
         A.read_begin = 0;
         A.read_end = total_reads;
+        if (interrupt) {
+            *ctx->h_iflag = 0;
+            A.interrupt_flag = ctx->d_iflag;
+        }
         QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
         QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
         void *args[] = {&A};
@@ -1909,6 +1935,26 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         }
         if (st) st->anneal_launches++;
         done = total_reads;
+        if (interrupt) {   // poll the callback while the launch runs; CTAs stop pulling work once the flag is up
+            QA_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+            for (;;) {
+                const cudaError_t q = cudaEventQuery(ctx->ev[3]);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) return fail(QA_ERR_CUDA, std::string("replay kernel: ") + cudaGetErrorString(q));
+                if (!interrupted && interrupt(iuser)) {
+                    *reinterpret_cast<volatile int *>(ctx->h_iflag) = 1;
+                    interrupted = true;
+                }
+                struct timespec ts = {0, 200000};
+                nanosleep(&ts, nullptr);
+            }
+            if (interrupted) {   // groups are handed out in read order: the first `pulled` groups are complete
+                unsigned long long pulled = 0;
+                QA_CUDA(cudaMemcpyAsync(&pulled, A.counter, sizeof(pulled), cudaMemcpyDeviceToHost, ctx->stream));
+                QA_CUDA(cudaStreamSynchronize(ctx->stream));
+                done = std::min<int64_t>(total_reads, (int64_t)std::min<unsigned long long>(pulled, (unsigned long long)total_items) * nw * 32);
+            }
+        }
     } else {
         // lockstep: one warp = 32 reads of one problem
         const bool pull = kernel == QA_KERNEL_LOCKSTEP_PULL;
@@ -1997,7 +2043,6 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         st->attempts += att * (uint64_t)num_betas * (uint64_t)sweeps_per_beta * (uint64_t)(done / P);
     }
     *completed = done;
-    (void)interrupted;
     return QA_OK;
 }
 
@@ -2120,6 +2165,9 @@ int qa_ctx_create(int device_id, qa_ctx **out) {
     QA_CUDA(cudaMalloc((void **)&ctx->d_flag, 2 * sizeof(int)));
     QA_CUDA(cudaMalloc((void **)&ctx->d_best_e, sizeof(double)));
     QA_CUDA(cudaMalloc((void **)&ctx->d_best_i, sizeof(long long)));
+    QA_CUDA(cudaHostAlloc((void **)&ctx->h_iflag, sizeof(int), cudaHostAllocMapped));
+    *ctx->h_iflag = 0;
+    QA_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_iflag, ctx->h_iflag, 0));
     *out = ctx;
     return QA_OK;
 }
@@ -2134,6 +2182,7 @@ int qa_ctx_destroy(qa_ctx *ctx) {
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_best_e) cudaFree(ctx->d_best_e);
     if (ctx->d_best_i) cudaFree(ctx->d_best_i);
+    if (ctx->h_iflag) cudaFreeHost(ctx->h_iflag);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -8,44 +8,55 @@
 //
 // This kernel keeps the SAME arithmetic but changes when it happens.  Per read it stores
 //     f[v]  the local field h_v + sum_j J_vj s_j as of the LAST VISIT of v      (fp64, read-interleaved f[v][lane])
-//     S[v]  the spin, F[v] "v flipped at its last visit"                           (bit-packed, {S,F}[word][lane])
+//     D[v]  "spin is down", F[v] "v flipped at its last visit"   (bit-packed per 16 variables: one word per half-word and
+//           lane, bit 2i+1 = D, bit 2i = F of variable 16*hw + i)
 // Between two visits of v every neighbour u is visited exactly once, so the updates neal would have pushed into f[v] are
 //     + 2 s_u J_uv   for the flagged neighbours u > v (flipped later in the previous sweep), ascending u, then
 //     + 2 s_u J_uv   for the flagged neighbours u < v (flipped earlier in this sweep),       ascending u
 // -- the same fp64 additions in the same order (s_u is the spin after the flip; a neighbour cannot flip twice in that
 // window).  Replaying them at the visit gives bit-identical fields, decisions, RNG draws and final states, but the memory
-// traffic becomes sequential and fully coalesced: 8 B of field per attempt (+8 B when it changed) plus the {S,F} words of
+// traffic becomes sequential and fully coalesced: 8 B of field per attempt (+8 B when it changed) plus the {S|F} words of
 // the neighbour cells, instead of 16 B x 4 (sector granularity) per (flip, neighbour).
 // When flips become rare the cost balance inverts (a replay touches every neighbour of every variable, a push only the
 // neighbours of accepted flips), so once the CTA-wide acceptance of a sweep drops below P.switch_permille the tile runs one
 // catch-up pass (pending u > v updates only) and finishes the schedule pushing, as neal does.  Both forms are exact, so
 // the hand-over point does not influence the result.
 //
-// Coupling slabs: the host packs consecutive variables greedily into blocks (at most RP_D variables, RP_MAXBW foreign spin
-// words, RP_CAP entries, never across a 32-variable spin word) and builds one contiguous slab {RpHdr, RpEntry[]} per block
-// (replay order, 2J premultiplied, slot/bit of the neighbour's spin word).  All warps of a CTA walk the blocks together; slabs are brought
-// into a 4-stage shared-memory ring with cp.async.bulk (TMA 1-D) completing on mbarriers, and released by one mbarrier arrive
-// per warp -- no __syncthreads in the sweep.  There is no fixed producer: whichever warp first gets within RP_DIST blocks of a
-// slab that has not been requested yet claims it (one shared-memory CAS) and issues the copy, so the ring runs at the pace
-// of the fastest warp and nobody waits for a particular (possibly de-prioritised) warp.
+// Blocks.  The host packs consecutive variables greedily into blocks (at most RP_D = 16 variables inside ONE 16-variable
+// half-word, RP_MAXBW foreign half-words, RP_CAP entry slots) and builds one contiguous slab {RpHdr, RpEntry[]} per block.
+// A row's entries are split where the data dependence is:
+//     pre part   neighbours u > v (ascending) then neighbours u < v0 (ascending): everything that is known when the block
+//                starts -- padded to rounds of 4 entries (padding: flag mask 0)
+//     seq part   neighbours v0 <= u < v (ascending): decided inside this block, read from the REGISTER that holds the
+//                block's own {S|F} word
+// so a block runs in two phases: a BATCH phase that streams the pre parts of all rows (no dependence on this block's
+// decisions: table loads run one round ahead, 6 instructions per entry: LDS.128 entry, LOP3 slot address, LDS word, SHF,
+// LOP3, DFMA -- see rp_add_entry) and leaves the partial sums in shared memory, and a SEQUENTIAL
+// phase (seq entries + neal's Metropolis decision per variable).  The foreign half-words of block b+1 are copied into the
+// warp's slot region by cp.async while block b is in its sequential phase (which does not read the slots); the only word
+// that can be stale in that copy -- block b's own -- is patched from the register when block b+1 starts.
+//
+// All warps of a CTA walk the blocks together; slabs are brought into a 4-stage shared-memory ring with cp.async.bulk
+// (TMA 1-D) completing on mbarriers, and released by one mbarrier arrive per warp -- no __syncthreads in the sweep.  There
+// is no fixed producer: whichever warp first gets within RP_DIST blocks of a slab that has not been requested yet claims it
+// (one shared-memory CAS) and issues the copy.
 #pragma once
 
-#ifndef RP_D
-#define RP_D 16       // variables per block, at most
-#endif
-constexpr int RP_SLOTS = 2 * RP_D;            // spin-word slots per warp: slot 0 = the block's own word
-constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign spin words per block
-constexpr int RP_CAP = 28 * RP_D;             // entries per slab
+constexpr int RP_D = 16;                      // variables per block, at most (= one half-word of spins)
+constexpr int RP_SLOTS = 32;                  // half-word slots per warp: slot 0 = the block's own half-word
+constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign half-words per block
+constexpr int RP_CAP = 448;                   // entry slots per slab (pre parts in rounds of 4, then the seq parts)
 constexpr int RP_STAGES = 4;      // power of two: stage = g & 3, phase = (g >> 2) & 1 for the running block counter g
 #ifndef RP_LA
-#define RP_LA 2     // local fields are loaded this many variables ahead of their visit
+#define RP_LA 4     // local fields are loaded this many rows ahead of their use in the batch phase
 #endif
 #ifndef RP_PF_DIST
 #define RP_PF_DIST 32   // L2 run-ahead of the field rows, in variables
 #endif
 constexpr int RP_DIST = 2;        // slabs are requested this many blocks ahead of the first warp that will need them
-constexpr int RP_WARP_BYTES = RP_SLOTS * 32 * 8;  // per warp: {~S,F}[slot][lane]; the push phase stages its fields here
-constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 8;
+constexpr int RP_SF_BYTES = RP_SLOTS * 32 * 4;   // per warp: {S | F << 16}[slot][lane]; 4 KB, aligned to its size
+constexpr int RP_PS_BYTES = RP_D * 32 * 8;       // per warp: partial sums [row][lane] (push phase: the block's fields)
+constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 7;
 #ifndef RP_MAX_WARPS
 #define RP_MAX_WARPS 8    // warps per CTA (upper bound; the host picks a power of two)
 #endif
@@ -54,29 +65,33 @@ constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 8;
 #endif
 
 struct alignas(16) RpHdr {
-    int32_t nent;               // entries in this slab
-    int32_t nbw;                // distinct neighbour words other than the block's own word
+    int32_t nent;               // entry slots in this slab (pre region incl. padding, then seq region)
+    int32_t nbw;                // distinct neighbour half-words other than the block's own
     int32_t v0;                 // first variable of the block
-    int32_t nv;                 // variables in the block (1 .. RP_D; v0 .. v0+nv-1 lie in one 32-variable spin word)
-    uint32_t row[RP_D];         // entry range of variable i: start | (end << 16)
-    uint16_t nlater[RP_D];      // leading entries of row i that refer to later variables (u > v)
-    uint16_t deg[RP_D];
+    int32_t nv;                 // variables in the block (1 .. RP_D; v0 .. v0+nv-1 lie in one 16-variable half-word)
+    int32_t prev_slot;          // slot holding the PREVIOUS block's half-word (0: not referenced / same half-word / first block)
+    int32_t seq_off;            // entry slot where the seq region starts (multiple of 4)
+    int32_t nbw_next;           // the half-word list of the NEXT block (cyclic): staged while this block decides
+    int32_t pad_;
+    uint32_t rowa[RP_D];        // pre rounds (bits 0-7) | seq entries (8-15) | degree (16-31)
+    uint32_t rowb[RP_D];        // later entries u > v (0-15) | pre entries without padding (16-31)
     int32_t ga[RP_D];           // group (low byte, 255: none) | coefficient << 8
-    int32_t bw[RP_MAXBW];       // neighbour word indices, slot s+1 holds word bw[s]
-    int32_t nbw_next;           // the same list for the NEXT block (cyclic): L2 run-ahead of its {S,F} rows
-    int32_t bw_next[RP_MAXBW];
+    int32_t bw[RP_SLOTS];       // neighbour half-word indices, slot s+1 holds half-word bw[s]
+    int32_t bw_next[RP_SLOTS];
 };
 static_assert(sizeof(RpHdr) % 16 == 0, "slab header layout");
 constexpr uint32_t RP_H_NBW = offsetof(RpHdr, nbw), RP_H_V0 = offsetof(RpHdr, v0), RP_H_NV = offsetof(RpHdr, nv),
-                   RP_H_ROW = offsetof(RpHdr, row), RP_H_NLATER = offsetof(RpHdr, nlater),
-                   RP_H_DEG = offsetof(RpHdr, deg), RP_H_GA = offsetof(RpHdr, ga), RP_H_BW = offsetof(RpHdr, bw),
-                   RP_H_NBWN = offsetof(RpHdr, nbw_next), RP_H_BWN = offsetof(RpHdr, bw_next);
+                   RP_H_PREV = offsetof(RpHdr, prev_slot), RP_H_SEQ = offsetof(RpHdr, seq_off),
+                   RP_H_ROWA = offsetof(RpHdr, rowa), RP_H_ROWB = offsetof(RpHdr, rowb), RP_H_GA = offsetof(RpHdr, ga),
+                   RP_H_BW = offsetof(RpHdr, bw), RP_H_NBWN = offsetof(RpHdr, nbw_next), RP_H_BWN = offsetof(RpHdr, bw_next);
 struct __align__(16) RpEntry {
-    double J2;     // 2 * J
-    int32_t j;     // neighbour (local variable index)
-    uint32_t B;    // bits 0-4: 31 - (j & 31); bits 8-12: slot; bit 15: neighbour inside the same block
+    double J;      // the coupling (0.0 for padding entries: fma(0, sigma, f) == f)
+    uint32_t zero; // low word of sigma: the entry's LDS.128 delivers the register pair {0, B} the DFMA multiplies by
+    uint32_t B;    // bits 0-4: 30 - 2 * (j & 15) (left shift that brings the neighbour's D bit to bit 31, its F bit to bit 30);
+                   // bits 7-11: slot; bits 12-31: neighbour j (local variable index, < 2^20)
 };
-constexpr int RP_STAGE_BYTES = (int)sizeof(RpHdr) + RP_CAP * (int)sizeof(RpEntry);
+constexpr int RP_MAX_VARS = 1 << 20;
+constexpr int RP_STAGE_BYTES = (int)sizeof(RpHdr) + (RP_CAP + 8) * (int)sizeof(RpEntry);   // + two rounds of read-ahead slack
 static_assert(RP_STAGE_BYTES % 16 == 0, "stage alignment");
 
 // ---- mbarrier / TMA 1-D primitives -----------------------------------------------------------------------------------
@@ -108,9 +123,9 @@ __device__ __forceinline__ int4 lds_v4(uint32_t a) {
     asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
     return r;
 }
-__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
-    uint2 r;
-    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+__device__ __forceinline__ uint32_t lds_vu32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
     return r;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -118,25 +133,32 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
     return r;
 }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
-    uint32_t r;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y));
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t x) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t a) {
     double r;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
     return r;
 }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
-// f += d on the lanes whose flag word has its top bit set (one predicated DADD: the only serial dependence of a replay)
-__device__ __forceinline__ void add_f64_if_neg(double &f, double d, uint32_t t) {
-    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(f) : "d"(d), "r"(t));
+// 16-byte asynchronous copy global (L2) -> shared (LDGSTS.BYPASS): no register staging, completion by cp.async.wait_all
+__device__ __forceinline__ void rp_cp_async16(uint32_t dst_s, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rp_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One replay entry: f += (neighbour up ? +2J : -2J) on the lanes whose copy of the neighbour's word has the F bit set.
+// One shift brings the neighbour's (D, F) bit pair to bits (31, 30); those two bits ARE the high word of a double sigma:
+// sign = D, exponent field 0x400 or 0 -> sigma = +-2.0 (flagged) or +-0.0 (not flagged).  fma(J, sigma, f) has an exact
+// product and ONE rounding: bit-identical to neal's  f += 4 s J s_j / (-2 s)  addition of +-2J, and the exact identity for
+// an unflagged neighbour (a zero field may change its sign, which no decision can observe: dE = -+2f is compared with
+// >= thr and <= 0 only).  SHF, LOP3, DFMA -- the DFMA chain is the only serial dependence of a replay.
+__device__ __forceinline__ void rp_add_entry(double &f, const int4 &q, uint32_t w) {
+    const uint32_t x = w << ((uint32_t)q.w & 31u);
+    f = fma(__hiloint2double(q.y, q.x), __hiloint2double((int)(x & 0xC0000000u), q.z), f);   // q.z == 0
 }
 
 struct RpCtx {
@@ -148,8 +170,9 @@ struct RpCtx {
     uint32_t gb;                         // running index of the next block this warp consumes
     // per lane
     double *fT;                          // f[v][lane], this lane's column
-    uint2 *SF;                           // {S,F}[word][lane], this lane's column
-    uint32_t sfbase_s;                   // shared address of this lane's column in the warp's size-aligned region
+    uint32_t *SF;                        // {S | F << 16}[half-word][lane], this lane's column
+    uint32_t sfb_s;                      // shared address of this lane's column in the warp's slot region (4 KB aligned + 4 * lane)
+    uint32_t psb_s;                      // shared address of this lane's column in the warp's partial-sum region
     int *Mcol;
     int mstride;
     const double *lam;
@@ -159,10 +182,6 @@ struct RpCtx {
     LaneStats st;
     bool active;
     int n, nblk, npad;
-#ifdef QA_RP_PROFILE
-    unsigned long long t_full, t_empty;  // cycles spent waiting for a slab / for a free stage
-    unsigned long long t_setup, t_prol, t_ent, t_dec, t_pass, t_flip;
-#endif
 };
 
 // lane 0 of any warp: request every slab up to running index `tgt` that nobody has requested yet.  `blk` is the block the
@@ -175,13 +194,7 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
             int b = blk + (int)(cur - c.gb);
             while (b >= c.nblk) b -= c.nblk;
             const uint32_t st = cur & (RP_STAGES - 1), ph = (cur / RP_STAGES) & 1u;
-#ifdef QA_RP_PROFILE
-            const long long t0 = clock64();
-#endif
             mbar_wait(c.empty_s + 8u * st, ph ^ 1u);     // every warp has released the previous use of that stage
-#ifdef QA_RP_PROFILE
-            c.t_empty += (unsigned long long)(clock64() - t0);
-#endif
             const uint32_t o0 = __ldg(c.off + b), o1 = __ldg(c.off + b + 1);
             const uint32_t bytes = (o1 - o0) * 16u;
             mbar_expect_tx(c.full_s + 8u * st, bytes);
@@ -193,28 +206,51 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
     }
 }
 
-// One pass over all blocks.  MODE 0: replay sweep (pull).  MODE 1: catch-up (pending later-neighbour updates only, no
-// decisions).  MODE 2: push sweep (neal's eager form).  MODE 3: field set-up f[v] = h_v + sum_j J_vj s_j in neal's
-// get_flip_energy order, for models whose adjacency lists are ascending (then adjacency order = the slab's earlier part
-// followed by its later part).  Returns the number of accepted flips of the warp.
+// the warp's rows of the foreign half-words listed at shared address `list_s` -> slots 1 .. nb (asynchronous).  A slot is one
+// 128-byte row [lane] in shared memory exactly as in global memory, so the warp copies four rows per instruction (8 lanes x
+// 16 bytes each); every lane later reads only its own column.
+__device__ __forceinline__ void rp_stage_issue(const RpCtx &c, uint32_t list_s, int nb) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t dst = c.sfb_s - 4u * lane + 128u + (lane >> 3) * 128u + (lane & 7u) * 16u;
+    const uint32_t *src = c.SF - lane + (lane & 7u) * 4u;
+    __syncwarp();   // every lane has finished reading the slots of the previous block
+    for (int s0 = 0; s0 < nb; s0 += 4) {
+        const int s = s0 + (int)(lane >> 3);
+        if (s < nb) {
+            const uint32_t w = lds_u32(list_s + 4u * (uint32_t)s);
+            rp_cp_async16(dst + (uint32_t)s0 * 128u, src + (int64_t)w * 32);
+        }
+    }
+}
+// wait for the staged rows (own copies), make them visible to the other lanes
+__device__ __forceinline__ void rp_stage_wait() {
+    rp_cp_async_wait_all();
+    __syncwarp();
+}
+
+// One pass over all blocks.  MODE 0: replay sweep.  MODE 1: catch-up (pending later-neighbour updates only, no decisions).
+// MODE 2: push sweep (neal's eager form).  MODE 3: field set-up f[v] = h_v + sum_j J_vj s_j in neal's get_flip_energy order,
+// for models whose adjacency lists are ascending (then adjacency order = pre entries u < v0, seq entries, later entries).
 // GROUPS: 0 none, 1 rank-1 groups with 32-bit exact integer arithmetic (host-checked ranges), 2 with 64-bit.
-// VAR: blocks of variable size (read from the slab header); false = every block holds exactly RP_D variables, which lets the
-// compiler keep the block geometry in immediates (22 % faster on config 3: the kernel sits at the 128-register limit).
-template <int MODE, int GROUPS, bool VAR>
-__device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
+template <int MODE, int GROUPS>
+__device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
     const int lane = threadIdx.x & 31;
     const double thr = 44.36142 / beta;
     const int n = c.n, nblk = c.nblk;
     double *const fT = c.fT;
-    uint2 *const SF = c.SF;
-    const uint32_t sfb = c.sfbase_s;
+    uint32_t *const SF = c.SF;
+    const uint32_t sfb = c.sfb_s, psb = c.psb_s;
     const bool active = c.active;
-    unsigned sweep_acc = 0;
-    uint32_t S = 0xffffffffu, F = 0u, S0 = 0xffffffffu, F0 = 0u;
+    uint32_t W = 0u, W0 = 0u, Wprev = 0u;   // the block's own half-word: bit 2i+1 = D (spin down), bit 2i = F (flipped)
 
-#ifdef QA_RP_PROFILE
-    const long long tp0 = clock64();
-#endif
+    double fq[RP_LA];   // fields of the next RP_LA rows of the batch phase
+#pragma unroll
+    for (int k = 0; k < RP_LA; ++k) fq[k] = 0.0;
+    if (MODE <= 1) {    // rows 0 .. RP_LA-1 of block 0 (every problem has at least one full half-word of padded variables)
+#pragma unroll
+        for (int k = 0; k < RP_LA; ++k) fq[k] = __ldcg(fT + k * 32);
+    }
+
     const uint32_t g_last = c.gb + (uint32_t)nblk - 1u;   // running index of the last block of this pass
     for (int blk = 0; blk < nblk; ++blk) {
         const uint32_t stage = c.gb & (RP_STAGES - 1), phase = (c.gb / RP_STAGES) & 1u;
@@ -224,269 +260,303 @@ __device__ unsigned rp_pass(RpCtx &c, double beta, bool has_next_pass) {
             rp_request(c, tgt, blk);
         }
         __syncwarp();
-#ifdef QA_RP_PROFILE
-        const long long tw0 = clock64();
-#endif
         mbar_wait(c.full_s + 8u * stage, phase);
-#ifdef QA_RP_PROFILE
-        if (lane == 0) c.t_full += (unsigned long long)(clock64() - tw0);
-#endif
         const uint32_t hdr = c.stage_s + stage * (uint32_t)RP_STAGE_BYTES;   // shared address of the slab
         const uint32_t ent = hdr + (uint32_t)sizeof(RpHdr);
-        const int v0 = VAR ? (int)lds_u32(hdr + RP_H_V0) : blk * RP_D;
-        const int nv = VAR ? (int)lds_u32(hdr + RP_H_NV) : RP_D;
-        const int wi = v0 >> 5;
-        const int sub = v0 & 31;
+        const int v0 = (int)lds_u32(hdr + RP_H_V0);
+        const int nv = (int)lds_u32(hdr + RP_H_NV);
+        const int hw = v0 >> 4;
+        const int sub = v0 & 15;
         double *const fB = fT + (int64_t)v0 * 32;
+        const int ilim = min(nv, n - v0);   // uniform: padding variables are not visited
         if (sub == 0) {
-            const uint2 own = __ldcg(SF + (int64_t)wi * 32);
-            S = own.x; F = own.y; S0 = S; F0 = F;
+            W = __ldcg(SF + (int64_t)hw * 32);
+            W0 = W;
         }
-#ifndef RP_NO_PREFETCH
-        {   // L2 run-ahead of the field rows RP_PF_DIST blocks on: 16 rows x 256 B = 128 sectors, one sector per lane and instruction
+        {   // L2 run-ahead of the field rows RP_PF_DIST variables on: 16 rows x 256 B = 128 sectors, one per lane and instruction
             int pv = (v0 & ~(RP_D - 1)) + RP_PF_DIST;   // a 16-row group ahead (wraps into the next sweep)
-            const int npad = VAR ? c.npad : nblk * RP_D;
-            if (pv >= npad) pv -= npad;
+            if (pv >= c.npad) pv -= c.npad;
             const char *pa = reinterpret_cast<const char *>(fT - lane + (int64_t)pv * 32) + lane * 32;
 #pragma unroll
             for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + k * 1024));
         }
-        if (MODE <= 1 || MODE == 3) {   // ... and of the {S,F} rows the next block will stage (8 sectors per word)
-            const int ns = (int)lds_u32(hdr + RP_H_NBWN) * 8;
-            const char *sfrow = reinterpret_cast<const char *>(SF - lane);
-            for (int k = lane; k < ns; k += 32) {
-                const int64_t w = (int64_t)lds_u32(hdr + RP_H_BWN + 4u * (uint32_t)(k >> 3));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + w * 256 + (k & 7) * 32));
-            }
-            if (sub != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sfrow + (int64_t)((wi + 1) * 32 < (VAR ? c.npad : nblk * RP_D) ? wi + 1 : 0) * 256 + (lane & 7) * 32));
+        if (MODE != 2) {
+            // the foreign half-words were requested while the previous block decided; the first block of a pass asks now
+            if (blk == 0) rp_stage_issue(c, hdr + RP_H_BW, (int)lds_u32(hdr + RP_H_NBW));
+            rp_stage_wait();
+            const uint32_t ps = lds_u32(hdr + RP_H_PREV);
+            if (blk != 0 && ps != 0u) sts_u32(sfb + ps * 128u, Wprev);   // the one word that copy could not have up to date
+            sts_u32(sfb, W);
         }
-#endif
-        bool blk_dirty = false;
-        if (MODE <= 1 || MODE == 3) {
-            // this lane's copy of every spin/flag word the block refers to (~S so that a set top bit means "spin down")
-            const int nbw = (int)lds_u32(hdr + RP_H_NBW);
-            for (int s = 0; s < nbw; s += 8) {
-                uint2 t[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (s + q < nbw) t[q] = __ldcg(SF + (int64_t)lds_u32(hdr + RP_H_BW + 4u * (uint32_t)(s + q)) * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (s + q < nbw) sts_u2(sfb + (uint32_t)(s + q + 1) * 256u, ~t[q].x, t[q].y);
-            }
-            sts_u2(sfb, ~S, F);
-        } else {
-            double t[RP_D];
-#pragma unroll
-            for (int i = 0; i < RP_D; ++i)
-                if (i < nv) t[i] = __ldcg(fB + i * 32);
-#pragma unroll
-            for (int i = 0; i < RP_D; ++i)
-                if (i < nv) sts_f64(sfb + (uint32_t)i * 256u, t[i]);
-        }
-        double fq[RP_LA];   // fields of the next RP_LA variables, loaded ahead of their visit
-#pragma unroll
-        for (int k = 0; k < RP_LA; ++k) fq[k] = 0.0;
-        if (MODE <= 1) {
-#pragma unroll
-            for (int k = 0; k < RP_LA; ++k)
-                if (k < nv) fq[k] = __ldcg(fB + k * 32);
-        }
-        const int ilim = min(nv, n - v0);   // uniform: padding variables are not visited
-#ifdef QA_RP_PROFILE
-        c.t_prol += (unsigned long long)(clock64() - tw0) ;
-#endif
 
-        for (int i = 0; i < ilim; ++i) {
-            const uint32_t rw = lds_u32(hdr + RP_H_ROW + 4u * (uint32_t)i);
-            const uint32_t a0 = ent + (rw & 0xffffu) * 16u;
-            const uint32_t bit = 1u << (sub + i);
-            const bool up = (S & bit) != 0u;
-            double fv;
-            if (MODE == 3) {
-                // h_v, then the earlier neighbours (ascending), then the later ones: 0.5 * (+-2J) is exact, one rounding per term
-                fv = __ldg(c.h + v0 + i);
-                const uint32_t am = a0 + (lds_u16(hdr + RP_H_NLATER + 2u * (uint32_t)i) & 0xfffu) * 16u;
-                const uint32_t a1 = ent + (rw >> 16) * 16u;
-                auto add1 = [&](const int4 &q, const uint2 &sf) {
-                    const uint32_t sg = __funnelshift_l(0u, sf.x, (uint32_t)q.w) & 0x80000000u;   // spin down: -J
-                    fv = fma(__hiloint2double(q.y ^ (int)sg, q.x), 0.5, fv);
-                };
+        if (MODE == 0) {
+            // ---- batch phase: pre parts of all rows; table entries are loaded one round ahead of their use (two buffers, rounds
+            // in pairs: no register rotation); rows in groups of RP_LA so that the field look-ahead needs no rotation either
+            uint32_t a = ent;
+            uint32_t chg = 0u;
+#pragma unroll 1
+            for (int i0 = 0; i0 < nv; i0 += RP_LA) {
 #pragma unroll
-                for (int seg = 0; seg < 2; ++seg) {
-                    uint32_t a = seg == 0 ? am : a0;
-                    const uint32_t ae = seg == 0 ? a1 : am;
-                    for (; a + 64u <= ae; a += 64u) {
-                        int4 q[4];
-                        uint2 sf[4];
+                for (int kk = 0; kk < RP_LA; ++kk) {
+                    const int i = i0 + kk;
+                    if (i < nv) {
+                        double p = fq[kk];
+                        if (i + RP_LA < nv) fq[kk] = __ldcg(fB + (i + RP_LA) * 32);
+                        const double f0 = p;
+                        const int nr = (int)(lds_u32(hdr + RP_H_ROWA + 4u * (uint32_t)i) & 255u);
+                        int4 qa[4], qb[4];
+                        uint32_t w[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) q[k] = lds_v4(a + 16u * k);
+                        for (int k = 0; k < 4; ++k) qa[k] = lds_v4(a + 16u * k);
+                        int r = 0;
+#pragma unroll 1
+                        for (; r + 2 <= nr; r += 2) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) sf[k] = lds_u2(((uint32_t)q[k].w & RP_SLOT_MASK) | sfb);
+                            for (int k = 0; k < 4; ++k) qb[k] = lds_v4(a + 64u + 16u * k);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) add1(q[k], sf[k]);
-                    }
-                    for (; a < ae; a += 16u) {
-                        const int4 q = lds_v4(a);
-                        add1(q, lds_u2(((uint32_t)q.w & RP_SLOT_MASK) | sfb));
-                    }
-                }
-                __stcg(fB + i * 32, fv);
-                continue;
-            } else if (MODE <= 1) {
-                fv = fq[0];
+                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qa[k].w & RP_SLOT_MASK) | sfb);
 #pragma unroll
-                for (int k = 0; k + 1 < RP_LA; ++k) fq[k] = fq[k + 1];
-                if (i + RP_LA < nv) fq[RP_LA - 1] = __ldcg(fB + (i + RP_LA) * 32);
-                const double f0 = fv;
-#ifdef QA_RP_PROFILE
-                const long long te0 = clock64();
-#endif
-                // a neighbour that did not flip contributes -0.0, the exact additive identity: the only serial dependence of
-                // a replay is one DADD per entry
-                auto replay1 = [&](const int4 &q, const uint2 &sf) {
-                    const uint32_t B = (uint32_t)q.w;
-                    const uint32_t sg = __funnelshift_l(0u, sf.x, B) & 0x80000000u;   // spin down: add -2J
-                    const bool flagged = (int)__funnelshift_l(0u, sf.y, B) < 0;
-                    const int hi = flagged ? (q.y ^ (int)sg) : (int)0x80000000u;
-                    const int lo = flagged ? q.x : 0;
-                    fv += __hiloint2double(hi, lo);
-                };
-                const uint32_t a1 = (MODE == 0) ? ent + (rw >> 16) * 16u
-                                                : a0 + lds_u16(hdr + RP_H_NLATER + 2u * (uint32_t)i) * 16u;
-                uint32_t a = a0;
-                // four entries per round: table entries first, then the lane's {~S,F} words, then the ordered additions
-                for (; a + 64u <= a1; a += 64u) {
-                    int4 q[4];
-                    uint2 sf[4];
+                            for (int k = 0; k < 4; ++k) rp_add_entry(p, qa[k], w[k]);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) q[k] = lds_v4(a + 16u * k);
+                            for (int k = 0; k < 4; ++k) qa[k] = lds_v4(a + 128u + 16u * k);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) sf[k] = lds_u2(((uint32_t)q[k].w & RP_SLOT_MASK) | sfb);
+                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qb[k].w & RP_SLOT_MASK) | sfb);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) replay1(q[k], sf[k]);
-                }
-                for (; a < a1; a += 16u) {
-                    const int4 q = lds_v4(a);
-                    const uint2 sf = lds_u2(((uint32_t)q.w & RP_SLOT_MASK) | sfb);
-                    replay1(q, sf);
-                }
-                if (fv != f0) __stcg(fB + i * 32, fv);
-#ifdef QA_RP_PROFILE
-                c.t_ent += (unsigned long long)(clock64() - te0);
-#endif
-                if (MODE == 1) continue;
-            } else {
-                fv = lds_f64(sfb + (uint32_t)i * 256u);
-            }
-#ifdef QA_RP_PROFILE
-            const long long td0 = clock64();
-#endif
-            double dE = up ? -2.0 * fv : 2.0 * fv;
-            int g = 255, a = 0;
-            if (GROUPS) {
-                const int ga = (int)lds_u32(hdr + RP_H_GA + 4u * (uint32_t)i);
-                g = ga & 255;
-                if (g != 255) {
-                    a = ga >> 8;
-                    if (GROUPS == 1) {
-                        const int m = c.Mcol[g * c.mstride] + reinterpret_cast<const int *>(c.kap)[2 * g];
-                        const int t = a * (a - (up ? m : -m));
-                        dE = dE + c.lam[g] * (double)t;
-                    } else {
-                        const long long t = (long long)a * ((long long)a - (up ? 1 : -1) * ((long long)c.Mcol[g * c.mstride] + c.kap[g]));
-                        dE = dE + c.lam[g] * (double)t;
+                            for (int k = 0; k < 4; ++k) rp_add_entry(p, qb[k], w[k]);
+                            a += 128u;
+                        }
+                        if (r < nr) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qa[k].w & RP_SLOT_MASK) | sfb);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) rp_add_entry(p, qa[k], w[k]);
+                            a += 64u;
+                        }
+                        sts_f64(psb + (uint32_t)i * 256u, p);
+                        if (p != f0) chg |= 1u << i;
                     }
                 }
             }
-            const bool cand = active && !(dE >= thr);
-            bool acc = false;
-            if (__any_sync(FULL_MASK, cand)) {
-                if (cand) c.st.cand++;
-                acc = ls_accept(dE, cand, beta, c.s0, c.s1, c.st);
+            // the batch phase is the last reader of the slots: request the next block's half-words now, load its first fields
+            if (blk + 1 < nblk) {
+                rp_stage_issue(c, hdr + RP_H_BWN, (int)lds_u32(hdr + RP_H_NBWN));
+                const double *fN = fB + nv * 32;
+#pragma unroll
+                for (int k = 0; k < RP_LA; ++k) fq[k] = __ldcg(fN + k * 32);
             }
-#ifdef QA_RP_PROFILE
-            c.t_dec += (unsigned long long)(clock64() - td0);
-#endif
-            if (MODE == 0) {
+
+            // ---- sequential phase: in-block earlier neighbours from the register, then neal's decision
+            uint32_t as = ent + lds_u32(hdr + RP_H_SEQ) * 16u;
+#pragma unroll 1
+            for (int i = 0; i < ilim; ++i) {
+                const uint32_t ra = lds_u32(hdr + RP_H_ROWA + 4u * (uint32_t)i);
+                const double pv = lds_f64(psb + (uint32_t)i * 256u);
+                double fv = pv;
+                const uint32_t ae = as + ((ra >> 8) & 255u) * 16u;
+                for (; as + 16u < ae; as += 32u) {
+                    const int4 qa = lds_v4(as), qb = lds_v4(as + 16u);
+                    rp_add_entry(fv, qa, W);
+                    rp_add_entry(fv, qb, W);
+                }
+                if (as < ae) {
+                    const int4 qa = lds_v4(as);
+                    rp_add_entry(fv, qa, W);
+                    as += 16u;
+                }
+                if (((chg >> i) & 1u) != 0u || fv != pv) __stcg(fB + i * 32, fv);
+                const uint32_t fb = 1u << (2 * (sub + i)), db = fb << 1;
+                const bool up = (W & db) == 0u;
+                double dE = up ? -2.0 * fv : 2.0 * fv;
+                int g = 255, ca = 0;
+                if (GROUPS) {
+                    const int ga = (int)lds_u32(hdr + RP_H_GA + 4u * (uint32_t)i);
+                    g = ga & 255;
+                    if (g != 255) {
+                        ca = ga >> 8;
+                        if (GROUPS == 1) {
+                            const int m = c.Mcol[g * c.mstride] + reinterpret_cast<const int *>(c.kap)[2 * g];
+                            const int t = ca * (ca - (up ? m : -m));
+                            dE = dE + c.lam[g] * (double)t;
+                        } else {
+                            const long long t = (long long)ca * ((long long)ca - (up ? 1 : -1) * ((long long)c.Mcol[g * c.mstride] + c.kap[g]));
+                            dE = dE + c.lam[g] * (double)t;
+                        }
+                    }
+                }
+                const bool cand = active && !(dE >= thr);
+                bool acc = false;
+                if (__any_sync(FULL_MASK, cand)) {
+                    if (cand) c.st.cand++;
+                    acc = ls_accept(dE, cand, beta, c.s0, c.s1, c.st);
+                }
                 // F[v] := accepted (also when nothing was accepted: the flag of the previous visit must be cleared)
-                F = acc ? (F | bit) : (F & ~bit);
-                if (acc) S ^= bit;
-                sts_u2(sfb, ~S, F);
+                W = acc ? ((W | fb) ^ db) : (W & ~fb);
                 if (acc) {
                     c.st.acc++;
-                    c.st.nbr += (unsigned long long)lds_u16(hdr + RP_H_DEG + 2u * (uint32_t)i);
+                    c.st.nbr += (unsigned long long)(ra >> 16);
                     if (GROUPS) {
-                        if (g != 255) c.Mcol[g * c.mstride] -= 2 * a * (up ? 1 : -1);
-                    }
-                }
-                sweep_acc += __popc(__ballot_sync(FULL_MASK, acc));
-            } else {
-                const unsigned accm = __ballot_sync(FULL_MASK, acc);
-                if (accm == 0u) continue;
-                sweep_acc += __popc(accm);
-#ifdef QA_RP_PROFILE
-                const long long tf0 = clock64();
-#endif
-                const int sgn = up ? (int)0x80000000u : 0;   // f[j] += -2 s_v J
-                const uint32_t deg = lds_u16(hdr + RP_H_DEG + 2u * (uint32_t)i);
-                const uint32_t a1 = a0 + deg * 16u;
-#pragma unroll 4
-                for (uint32_t ad = a0; ad < a1; ad += 16u) {
-                    const int4 q = lds_v4(ad);
-                    const double d = __hiloint2double(q.y ^ sgn, q.x);
-                    if ((uint32_t)q.w & 0x8000u) {   // uniform: neighbour staged in this block
-                        const uint32_t ca = sfb + ((uint32_t)(q.z - v0) << 8);
-                        if (acc) sts_f64(ca, lds_f64(ca) + d);
-                        blk_dirty = true;
-                    } else {
-                        red_add_f64_if(fT + (int64_t)q.z * 32, d, acc);
-                    }
-                }
-#ifdef QA_RP_PROFILE
-                c.t_flip += (unsigned long long)(clock64() - tf0);
-#endif
-                if (acc) {
-                    S ^= bit;
-                    c.st.acc++;
-                    c.st.nbr += (unsigned long long)deg;
-                    if (GROUPS) {
-                        if (g != 255) c.Mcol[g * c.mstride] -= 2 * a * (up ? 1 : -1);
+                        if (g != 255) c.Mcol[g * c.mstride] -= 2 * ca * (up ? 1 : -1);
                     }
                 }
             }
-        }
-        if (MODE == 2) {
+        } else if (MODE == 1) {
+            // ---- catch-up: the pending later-neighbour updates (a prefix of every pre part), no decisions
+            uint32_t a = ent;
+#pragma unroll 1
+            for (int i0 = 0; i0 < nv; i0 += RP_LA) {
+#pragma unroll
+                for (int kk = 0; kk < RP_LA; ++kk) {
+                    const int i = i0 + kk;
+                    if (i < nv) {
+                        double p = fq[kk];
+                        if (i + RP_LA < nv) fq[kk] = __ldcg(fB + (i + RP_LA) * 32);
+                        const double f0 = p;
+                        const uint32_t nr = lds_u32(hdr + RP_H_ROWA + 4u * (uint32_t)i) & 255u;
+                        const uint32_t nl = lds_u32(hdr + RP_H_ROWB + 4u * (uint32_t)i) & 0xffffu;
+                        for (uint32_t k = 0; k < nl; ++k) {
+                            const int4 q = lds_v4(a + 16u * k);
+                            rp_add_entry(p, q, lds_vu32(((uint32_t)q.w & RP_SLOT_MASK) | sfb));
+                        }
+                        a += nr * 64u;
+                        if (p != f0) __stcg(fB + i * 32, p);
+                    }
+                }
+            }
+            if (blk + 1 < nblk) {
+                rp_stage_issue(c, hdr + RP_H_BWN, (int)lds_u32(hdr + RP_H_NBWN));
+                const double *fN = fB + nv * 32;
+#pragma unroll
+                for (int k = 0; k < RP_LA; ++k) fq[k] = __ldcg(fN + k * 32);
+            }
+        } else if (MODE == 3) {
+            // ---- set-up: h_v, then the earlier neighbours (pre entries u < v0, seq entries), then the later ones, ascending:
+            // neal's get_flip_energy order for ascending adjacency lists, one rounding per term.
+            uint32_t a = ent;
+            uint32_t as = ent + lds_u32(hdr + RP_H_SEQ) * 16u;
+#pragma unroll 1
+            for (int i = 0; i < nv; ++i) {
+                const uint32_t ra = lds_u32(hdr + RP_H_ROWA + 4u * (uint32_t)i);
+                const uint32_t rb = lds_u32(hdr + RP_H_ROWB + 4u * (uint32_t)i);
+                const uint32_t nl = rb & 0xffffu, np = rb >> 16, ns = (ra >> 8) & 255u;
+                if (i < ilim) {
+                    double fv = __ldg(c.h + v0 + i);
+                    auto add1 = [&](uint32_t ad) {
+                        const int4 q = lds_v4(ad);
+                        const uint32_t w = lds_vu32(((uint32_t)q.w & RP_SLOT_MASK) | sfb);
+                        const uint32_t x = w << ((uint32_t)q.w & 31u);
+                        fv = fv + __hiloint2double(q.y ^ (int)(x & 0x80000000u), q.x);   // down: -J
+                    };
+                    for (uint32_t k = nl; k < np; ++k) add1(a + 16u * k);
+                    for (uint32_t k = 0; k < ns; ++k) add1(as + 16u * k);
+                    for (uint32_t k = 0; k < nl; ++k) add1(a + 16u * k);
+                    __stcg(fB + i * 32, fv);
+                }
+                a += (ra & 255u) * 64u;
+                as += ns * 16u;
+            }
+            if (blk + 1 < nblk) rp_stage_issue(c, hdr + RP_H_BWN, (int)lds_u32(hdr + RP_H_NBWN));
+        } else {
+            // ---- push sweep: the block's fields staged in shared memory, neal's eager neighbour updates
+            {
+                double t[RP_D];
+#pragma unroll
+                for (int i = 0; i < RP_D; ++i)
+                    if (i < nv) t[i] = __ldcg(fB + i * 32);
+#pragma unroll
+                for (int i = 0; i < RP_D; ++i)
+                    if (i < nv) sts_f64(psb + (uint32_t)i * 256u, t[i]);
+            }
+            bool blk_dirty = false;
+            uint32_t a = ent;
+            uint32_t as = ent + lds_u32(hdr + RP_H_SEQ) * 16u;
+#pragma unroll 1
+            for (int i = 0; i < ilim; ++i) {
+                const uint32_t ra = lds_u32(hdr + RP_H_ROWA + 4u * (uint32_t)i);
+                const uint32_t a_row = a, as_row = as;
+                a += (ra & 255u) * 64u;
+                as += ((ra >> 8) & 255u) * 16u;
+                const double fv = lds_f64(psb + (uint32_t)i * 256u);
+                const uint32_t db = 2u << (2 * (sub + i));
+                const bool up = (W & db) == 0u;
+                double dE = up ? -2.0 * fv : 2.0 * fv;
+                int g = 255, ca = 0;
+                if (GROUPS) {
+                    const int ga = (int)lds_u32(hdr + RP_H_GA + 4u * (uint32_t)i);
+                    g = ga & 255;
+                    if (g != 255) {
+                        ca = ga >> 8;
+                        if (GROUPS == 1) {
+                            const int m = c.Mcol[g * c.mstride] + reinterpret_cast<const int *>(c.kap)[2 * g];
+                            const int t = ca * (ca - (up ? m : -m));
+                            dE = dE + c.lam[g] * (double)t;
+                        } else {
+                            const long long t = (long long)ca * ((long long)ca - (up ? 1 : -1) * ((long long)c.Mcol[g * c.mstride] + c.kap[g]));
+                            dE = dE + c.lam[g] * (double)t;
+                        }
+                    }
+                }
+                const bool cand = active && !(dE >= thr);
+                bool acc = false;
+                if (__any_sync(FULL_MASK, cand)) {
+                    if (cand) c.st.cand++;
+                    acc = ls_accept(dE, cand, beta, c.s0, c.s1, c.st);
+                }
+                if (__ballot_sync(FULL_MASK, acc) == 0u) continue;
+                const int sgn = up ? (int)0x80000000u : 0;   // f[j] += -2 s_v J
+                const uint32_t np = lds_u32(hdr + RP_H_ROWB + 4u * (uint32_t)i) >> 16;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t ab = part == 0 ? a_row : as_row;
+                    const uint32_t cnt = part == 0 ? np : ((ra >> 8) & 255u);
+#pragma unroll 4
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const int4 q = lds_v4(ab + 16u * k);
+                        const int j = (int)((uint32_t)q.w >> 12);
+                        const double d = __hiloint2double(q.y ^ sgn, q.x) * 2.0;   // exact
+                        if ((uint32_t)(j - v0) < (uint32_t)nv) {   // uniform: neighbour staged in this block
+                            const uint32_t cad = psb + ((uint32_t)(j - v0) << 8);
+                            if (acc) sts_f64(cad, lds_f64(cad) + d);
+                            blk_dirty = true;
+                        } else {
+                            red_add_f64_if(fT + (int64_t)j * 32, d, acc);
+                        }
+                    }
+                }
+                if (acc) {
+                    W ^= db;
+                    c.st.acc++;
+                    c.st.nbr += (unsigned long long)(ra >> 16);
+                    if (GROUPS) {
+                        if (g != 255) c.Mcol[g * c.mstride] -= 2 * ca * (up ? 1 : -1);
+                    }
+                }
+            }
             if (blk_dirty) {  // uniform: write the staged fields back (coalesced 256 B rows)
 #pragma unroll
                 for (int i = 0; i < RP_D; ++i)
-                    if (i < nv) __stcg(fB + i * 32, lds_f64(sfb + (uint32_t)i * 256u));
+                    if (i < nv) __stcg(fB + i * 32, lds_f64(psb + (uint32_t)i * 256u));
             }
         }
-        if (MODE != 1 && MODE != 3 && sub + nv == 32) {
-            if (S != S0 || F != F0) __stcg(SF + (int64_t)wi * 32, make_uint2(S, F));
+        if ((MODE == 0 || MODE == 2) && sub + nv == RP_D) {
+            if (W != W0) __stcg(SF + (int64_t)hw * 32, W);
         }
+        Wprev = W;
         // release the stage: one arrive per warp
         __syncwarp();
         if (lane == 0) mbar_arrive(c.empty_s + 8u * stage);
         ++c.gb;
     }
-#ifdef QA_RP_PROFILE
-    c.t_pass += (unsigned long long)(clock64() - tp0);
-#endif
-    return sweep_acc;
 }
 
 // The set-up pass as a real call with the context passed BY VALUE: its registers do not add to the pressure of the sweep
-// loops (the kernel sits at the 128-register limit and every spilled value there costs measurable time).
-template <bool VAR>
+// loops.
 __device__ __noinline__ uint32_t rp_setup_pass(RpCtx c) {
-    rp_pass<3, 0, VAR>(c, 1.0, true);
+    rp_pass<3, 0>(c, 1.0, true);
     return c.gb;
 }
 
-// local field of v in neal's get_flip_energy order (adjacency order), spins from the {S,F} scratch; loads batched by 8
-__device__ __forceinline__ double rp_field_direct(const ProblemDesc &D, const uint2 *SF, int v, int e0, int e1) {
+// local field of v in neal's get_flip_energy order (adjacency order), spins from the {S|F} scratch; loads batched by 8
+__device__ __forceinline__ double rp_field_direct(const ProblemDesc &D, const uint32_t *SF, int v, int e0, int e1) {
     double fv = __ldg(D.h + v);
     for (int e = e0; e < e1; e += 8) {
         int jq[8];
@@ -494,22 +564,23 @@ __device__ __forceinline__ double rp_field_direct(const ProblemDesc &D, const ui
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             jq[q] = __ldg(D.col + min(e + q, e1 - 1));
-            wq[q] = __ldcg(SF + (int64_t)(jq[q] >> 5) * 32).x;
+            wq[q] = __ldcg(SF + (int64_t)(jq[q] >> 4) * 32);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (e + q < e1) {
                 const double J = __ldg(D.val + e + q);
-                fv += ((wq[q] >> (jq[q] & 31)) & 1u) ? J : -J;
+                fv += ((wq[q] >> (2 * (jq[q] & 15) + 1)) & 1u) ? -J : J;
             }
         }
     }
     return fv;
 }
 
-// Shared-memory layout: [slab stages][mbarriers][CTA scratch][lambda][kappa][group counters] then, aligned to its size in the
-// shared window (so that a slot address is formed by OR), one RP_WARP_BYTES region per warp.  `smem_base` is the shared-window
-// offset of the dynamic allocation (1 KB on sm_100: the system-reserved bytes); the kernel verifies the assumption.
+// Shared-memory layout: [slab stages][mbarriers][CTA scratch][lambda][kappa][group counters] then, aligned to RP_SF_BYTES in
+// the shared window (so that a slot address is formed by OR), one slot region per warp, then one partial-sum region per warp.
+// `smem_base` is the shared-window offset of the dynamic allocation (1 KB on sm_100: the system-reserved bytes); the kernel
+// verifies the assumption.
 __host__ __device__ inline size_t rp_fixed_bytes(int nw, int max_groups) {
     size_t b = (size_t)RP_STAGES * RP_STAGE_BYTES + 8 * (2 * RP_STAGES) + 32;
     b += (sizeof(double) + sizeof(long long)) * (size_t)max_groups;
@@ -518,24 +589,25 @@ __host__ __device__ inline size_t rp_fixed_bytes(int nw, int max_groups) {
 }
 __host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned smem_base) {
     const size_t fixed = rp_fixed_bytes(nw, max_groups);
-    const size_t pad = (RP_WARP_BYTES - (smem_base + fixed) % RP_WARP_BYTES) % RP_WARP_BYTES;
-    return fixed + pad + (size_t)nw * RP_WARP_BYTES;
+    const size_t pad = (RP_SF_BYTES - (smem_base + fixed) % RP_SF_BYTES) % RP_SF_BYTES;
+    return fixed + pad + (size_t)nw * (RP_SF_BYTES + RP_PS_BYTES);
 }
 constexpr int QA_ERR_SMEM_BASE = -100;   // internal: the dynamic shared memory does not start where the host assumed
 
-template <int GROUPS, bool VAR>
+template <int GROUPS>
 __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_replay(AnnealParams P) {
     extern __shared__ __align__(16) unsigned char rp_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int NW = blockDim.x >> 5;
-    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(rp_raw);
+    uint32_t raw_s;   // opaque to the compiler: it would otherwise re-derive the window address (S2R + LEA) inside the hot loops
+    asm volatile("mov.u32 %0, %1;" : "=r"(raw_s) : "r"((uint32_t)__cvta_generic_to_shared(rp_raw)));
     const uint32_t fixed = (uint32_t)rp_fixed_bytes(NW, P.max_groups);
-    const uint32_t base_s = (raw_s + fixed + (uint32_t)RP_WARP_BYTES - 1u) & ~((uint32_t)RP_WARP_BYTES - 1u);    // warp regions
+    const uint32_t base_s = (raw_s + fixed + (uint32_t)RP_SF_BYTES - 1u) & ~((uint32_t)RP_SF_BYTES - 1u);    // warp regions
     {
         uint32_t dyn;
         asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-        if (base_s - raw_s + (uint32_t)NW * RP_WARP_BYTES > dyn) {   // uniform: report the real base and leave
+        if (base_s - raw_s + (uint32_t)NW * (RP_SF_BYTES + RP_PS_BYTES) > dyn) {   // uniform: report the real base and leave
             if (threadIdx.x == 0) {
                 P.error_flag[1] = (int)raw_s;
                 atomicExch(P.error_flag, QA_ERR_SMEM_BASE);
@@ -577,12 +649,8 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
     c.stage_s = raw_s;
     c.issued = issued_sh;
     c.gb = 0u;
-#ifdef QA_RP_PROFILE
-    c.t_full = 0ull;
-    c.t_empty = 0ull;
-    c.t_setup = c.t_prol = c.t_ent = c.t_dec = c.t_pass = c.t_flip = 0ull;
-#endif
-    c.sfbase_s = base_s + (uint32_t)wib * RP_WARP_BYTES + (uint32_t)lane * 8u;
+    c.sfb_s = base_s + (uint32_t)wib * RP_SF_BYTES + (uint32_t)lane * 4u;
+    c.psb_s = base_s + (uint32_t)NW * RP_SF_BYTES + (uint32_t)wib * RP_PS_BYTES + (uint32_t)lane * 8u;
     c.Mcol = M_all + threadIdx.x;
     c.mstride = (int)blockDim.x;
     c.lam = lam_sh;
@@ -590,11 +658,16 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
     c.st = {0, 0, 0, 0, 0};
     const int64_t slot = (int64_t)blockIdx.x * NW + wib;
     c.fT = P.fT_scratch + slot * P.fT_stride + lane;
-    c.SF = reinterpret_cast<uint2 *>(P.sf_scratch) + slot * P.sf_stride + lane;
+    c.SF = reinterpret_cast<uint32_t *>(P.sf_scratch) + slot * P.sf_stride + lane;
     int acc_par = 0;
 
     for (;;) {
-        if (threadIdx.x == 0) *item_sh = (long long)atomicAdd(P.counter, 1ull);
+        if (P.interrupt_flag != nullptr && threadIdx.x == 0) {   // host-mapped flag set by the caller's interrupt callback
+            if (*reinterpret_cast<const volatile int *>(P.interrupt_flag) != 0) *item_sh = (long long)P.total_items;
+            else *item_sh = (long long)atomicAdd(P.counter, 1ull);
+        } else if (threadIdx.x == 0) {
+            *item_sh = (long long)atomicAdd(P.counter, 1ull);
+        }
         __syncthreads();
         const int64_t item = *item_sh;
         __syncthreads();
@@ -616,37 +689,51 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
         const long long total_sweeps = (long long)P.num_betas * P.sweeps_per_beta;
         if (lane == 0 && total_sweeps > 0) rp_request(c, c.gb + (uint32_t)RP_DIST, 0);   // overlaps with the set-up below
 
-#ifdef QA_RP_PROFILE
-        const long long ts0 = clock64();
-#endif
         const unsigned long long sd = active ? P.seeds[D.read_base + r] : 1ull;
         c.s0 = sd ? sd : ~0ull;
         c.s1 = 0;
-        const int n = D.n, nch = D.nch;
-        // ---- pack this read's +-1 bytes (padding lanes and padding variables are +1), clear the flags
-        for (int wi = 0; wi < nch; ++wi) {
-            uint32_t w = 0xffffffffu;
-            if (active) {
-                const int8_t *row = D.states + r * (int64_t)n + wi * 32;
-                const int lim = min(32, n - wi * 32);
-                for (int i = 0; i < lim; ++i) {
-                    const int s = row[i];
-                    if (s != 1 && s != -1) atomicExch(P.error_flag, QA_ERR_STATE);
-                    if (s < 0) w &= ~(1u << i);
+        const int n = D.n, nhw = D.nch * 2;
+        // ---- pack this read's +-1 bytes into D bits (padding lanes and padding variables are +1: D = 0), clear the flags
+        {
+            const int8_t *row0 = D.states + r * (int64_t)n;
+            const bool vec = active && ((reinterpret_cast<uintptr_t>(row0) & 15u) == 0u);
+            for (int hw = 0; hw < nhw; ++hw) {
+                uint32_t w = 0u;
+                if (active) {
+                    const int8_t *row = row0 + hw * 16;
+                    const int lim = min(16, n - hw * 16);
+                    if (vec && lim == 16) {
+                        const int4 t = *reinterpret_cast<const int4 *>(row);
+                        const uint32_t tw[4] = {(uint32_t)t.x, (uint32_t)t.y, (uint32_t)t.z, (uint32_t)t.w};
+                        bool bad = false;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t neg = (tw[k] >> 7) & 0x01010101u;          // sign bit of every byte
+                            bad = bad || tw[k] != 0x01010101u + neg * 0xfeu;          // every byte 0x01 or 0xff
+                            w |= (((neg << 1) | (neg >> 5) | (neg >> 11) | (neg >> 17)) & 0xaau) << (8 * k);
+                        }
+                        if (bad) atomicExch(P.error_flag, QA_ERR_STATE);
+                    } else {
+                        for (int i = 0; i < lim; ++i) {
+                            const int s = row[i];
+                            if (s != 1 && s != -1) atomicExch(P.error_flag, QA_ERR_STATE);
+                            if (s < 0) w |= 2u << (2 * i);
+                        }
+                    }
                 }
+                __stcg(c.SF + (int64_t)hw * 32, w);
             }
-            __stcg(c.SF + (int64_t)wi * 32, make_uint2(w, 0u));
         }
         if (GROUPS) {
             for (int g = 0; g < D.ngroups; ++g) c.Mcol[g * c.mstride] = 0;
-            for (int wi = 0; wi < nch; ++wi) {
-                const uint32_t w = __ldcg(c.SF + (int64_t)wi * 32).x;
-                for (int i = 0; i < 32; ++i) {
-                    const int v = wi * 32 + i;
+            for (int hw = 0; hw < nhw; ++hw) {
+                const uint32_t w = __ldcg(c.SF + (int64_t)hw * 32);
+                for (int i = 0; i < 16; ++i) {
+                    const int v = hw * 16 + i;
                     const int g = __ldg(D.grp + v);  // uniform
                     if (g >= 0) {
                         const int a = __ldg(D.coef + v);
-                        c.Mcol[g * c.mstride] += ((w >> i) & 1u) ? a : -a;
+                        c.Mcol[g * c.mstride] += ((w >> (2 * i + 1)) & 1u) ? -a : a;
                     }
                 }
             }
@@ -654,7 +741,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
         // ---- local fields in neal's get_flip_energy order: through the slab ring when the adjacency lists are ascending,
         // else row by row from the CSR
         if (P.rp_slab_init) {
-            if (total_sweeps > 0) c.gb = rp_setup_pass<VAR>(c);
+            if (total_sweeps > 0) c.gb = rp_setup_pass(c);
         } else {
             int e0 = __ldg(D.rowptr);
             for (int v = 0; v < n; ++v) {
@@ -663,9 +750,6 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                 e0 = e1;
             }
         }
-#ifdef QA_RP_PROFILE
-        c.t_setup += (unsigned long long)(clock64() - ts0);
-#endif
         // ---- the schedule: replay sweeps while flips are frequent, then one catch-up pass and push sweeps
         bool push = false;
         long long done = 0;
@@ -679,31 +763,56 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                     printf("[qa sweep] %lld beta %.4g mode %s clock %lld\n", done, beta, push ? "push" : "replay", clock64());
 #endif
                 if (push) {
-                    rp_pass<2, GROUPS, VAR>(c, beta, more);
+                    rp_pass<2, GROUPS>(c, beta, more);
                 } else {
-                    const unsigned wacc = rp_pass<0, GROUPS, VAR>(c, beta, more);
+                    const unsigned acc0 = c.st.acc;
+                    rp_pass<0, GROUPS>(c, beta, more);
                     if (more) {  // CTA-uniform hand-over decision
+                        unsigned wacc = c.st.acc - acc0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) wacc += __shfl_xor_sync(FULL_MASK, wacc, o);
                         if (lane == 0) atomicAdd(acc_sh + acc_par, wacc);
                         __syncthreads();
                         const unsigned long long tot = acc_sh[acc_par];
                         if (threadIdx.x == 0) acc_sh[acc_par ^ 1] = 0u;
                         acc_par ^= 1;
                         if (tot * 1000ull < (unsigned long long)P.switch_permille * (unsigned long long)n * (unsigned long long)cta_reads) {
-                            rp_pass<1, 0, VAR>(c, beta, true);
+                            rp_pass<1, 0>(c, beta, true);
                             push = true;
                         }
                     }
                 }
             }
         }
-        // ---- final spins: packed transposed layout for the energy kernel, +-1 bytes for the caller
+        // ---- final spins: packed transposed layout for the energy kernel (bit = 1: spin up), +-1 bytes for the caller
         if (active) {
-            for (int wi = 0; wi < nch; ++wi) {
-                const uint32_t w = __ldcg(c.SF + (int64_t)wi * 32).x;
-                D.packedT[(int64_t)wi * D.rpad + r] = w;
-                int8_t *row = D.states + r * (int64_t)n + wi * 32;
-                const int lim = min(32, n - wi * 32);
-                for (int i = 0; i < lim; ++i) row[i] = ((w >> i) & 1u) ? 1 : -1;
+            int8_t *row0 = D.states + r * (int64_t)n;
+            const bool vec = (reinterpret_cast<uintptr_t>(row0) & 15u) == 0u;
+            uint32_t up32 = 0u;
+            for (int hw = 0; hw < nhw; ++hw) {
+                const uint32_t w = __ldcg(c.SF + (int64_t)hw * 32);
+                uint32_t x = (w >> 1) & 0x55555555u;           // the 16 D bits, compressed to the low half
+                x = (x | (x >> 1)) & 0x33333333u;
+                x = (x | (x >> 2)) & 0x0f0f0f0fu;
+                x = (x | (x >> 4)) & 0x00ff00ffu;
+                x = (x | (x >> 8)) & 0x0000ffffu;
+                const uint32_t up16 = ~x & 0xffffu;
+                if (hw & 1) D.packedT[(int64_t)(hw >> 1) * D.rpad + r] = up32 | (up16 << 16);
+                else up32 = up16;
+                int8_t *row = row0 + hw * 16;
+                const int lim = min(16, n - hw * 16);
+                if (vec && lim == 16) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t t = (w >> (8 * k)) & 0xaau;
+                        const uint32_t sp = ((t >> 1) | (t << 5) | (t << 11) | (t << 17)) & 0x01010101u;   // down flag per byte
+                        o[k] = 0x01010101u + sp * 0xfeu;
+                    }
+                    *reinterpret_cast<int4 *>(row) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+                } else {
+                    for (int i = 0; i < lim; ++i) row[i] = ((w >> (2 * i + 1)) & 1u) ? -1 : 1;
+                }
             }
         }
     }
@@ -712,19 +821,6 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
 #pragma unroll
     for (int q = 0; q < 5; ++q)
         for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL_MASK, v[q], off);
-#ifdef QA_RP_PROFILE
-    if (lane == 0) {   // development build: cycles spent waiting on the ring, reported through the otherwise unused counters
-        unsigned long long *dbg = P.stats + QA_NSTAT + 1;
-        atomicAdd(dbg + 0, c.t_setup);
-        atomicAdd(dbg + 1, c.t_full);
-        atomicAdd(dbg + 2, c.t_empty);
-        atomicAdd(dbg + 3, c.t_prol);
-        atomicAdd(dbg + 4, c.t_ent);
-        atomicAdd(dbg + 5, c.t_dec);
-        atomicAdd(dbg + 6, c.t_pass);
-        atomicAdd(dbg + 7, c.t_flip);
-    }
-#endif
     if (lane == 0) {
         atomicAdd(P.stats + ST_CAND, v[0]);
         atomicAdd(P.stats + ST_DRAWS, v[1]);

@@ -1,6 +1,7 @@
 """CPU tests of the replay kernel's host logic (csrc/qanneal.cu::pack_replay_slabs through the host-only C-ABI hook
 qa_debug_pack_slabs): block invariants of the coupling slabs, and -- the strong one -- a pure-Python replay that consumes
-ONLY the packed slabs (entry order, 2J values, tails) and must reproduce the oracle's final states bit for bit.
+ONLY the packed slabs in the kernel's two-phase order (pre parts of a block against the state at block start, then seq
+parts + decisions) and must reproduce the oracle's final states bit for bit.
 No GPU is needed: the hook makes no CUDA call."""
 import ctypes as C
 import math
@@ -11,12 +12,13 @@ import pytest
 from oracle import oracle
 from scrna_seq_qannealing_clustering_b200 import _lib, models, schedule, snn
 
-RP_D, RP_MAXBW, RP_CAP = 16, 31, 448
-HDR = np.dtype([("nent", "<i4"), ("nbw", "<i4"), ("v0", "<i4"), ("nv", "<i4"), ("row", "<u4", RP_D), ("nlater", "<u2", RP_D),
-                ("deg", "<u2", RP_D), ("ga", "<i4", RP_D), ("bw", "<i4", RP_MAXBW), ("nbw_next", "<i4"), ("bw_next", "<i4", RP_MAXBW),
-                ("pad", "<i4")])
-ENT = np.dtype([("J2", "<f8"), ("j", "<i4"), ("B", "<u4")])
-assert HDR.itemsize == 464 and ENT.itemsize == 16
+RP_D, RP_SLOTS, RP_CAP = 16, 32, 448
+RP_MAXBW = RP_SLOTS - 1
+HDR = np.dtype([("nent", "<i4"), ("nbw", "<i4"), ("v0", "<i4"), ("nv", "<i4"), ("prev_slot", "<i4"), ("seq_off", "<i4"),
+                ("nbw_next", "<i4"), ("pad", "<i4"), ("rowa", "<u4", RP_D), ("rowb", "<u4", RP_D), ("ga", "<i4", RP_D),
+                ("bw", "<i4", RP_SLOTS), ("bw_next", "<i4", RP_SLOTS)])
+ENT = np.dtype([("J", "<f8"), ("zero", "<u4"), ("B", "<u4")])
+assert HDR.itemsize == 480 and ENT.itemsize == 16
 
 
 def adjacency(n, starts, ends, weights):
@@ -62,40 +64,59 @@ def pack(model):
     return rows, blocks, bool(uni.value)
 
 
+def row_parts(hdr, ent, i):
+    """(pre entries without padding, padding entries, seq entries) of row i of a block, in slab order."""
+    pre0 = 4 * sum(int(hdr["rowa"][k]) & 255 for k in range(i))
+    rounds = int(hdr["rowa"][i]) & 255
+    npre = int(hdr["rowb"][i]) >> 16
+    seq0 = int(hdr["seq_off"]) + sum((int(hdr["rowa"][k]) >> 8) & 255 for k in range(i))
+    nseq = (int(hdr["rowa"][i]) >> 8) & 255
+    return ent[pre0:pre0 + npre], ent[pre0 + npre:pre0 + 4 * rounds], ent[seq0:seq0 + nseq]
+
+
 def check_invariants(model, rows, blocks):
     n = model.num_variables
-    npad = (n + 31) // 32 * 32
+    npad = (n + 15) // 16 * 16
     v = 0
     for b, (hdr, ent) in enumerate(blocks):
         v0, nv = int(hdr["v0"]), int(hdr["nv"])
-        assert v0 == v and 1 <= nv <= RP_D and (v0 >> 5) == ((v0 + nv - 1) >> 5), "blocks tile the variables inside one spin word"
-        assert int(hdr["nbw"]) <= RP_MAXBW and int(hdr["nent"]) <= RP_CAP
-        own = v0 >> 5
+        assert v0 == v and 1 <= nv <= RP_D and (v0 >> 4) == ((v0 + nv - 1) >> 4), "blocks tile the variables inside one half-word"
+        assert int(hdr["nbw"]) <= RP_MAXBW and int(hdr["nent"]) <= RP_CAP and int(hdr["seq_off"]) % 4 == 0
+        own = v0 >> 4
         words = list(hdr["bw"][: int(hdr["nbw"])])
         assert own not in words and len(set(words)) == len(words)
         nxt = blocks[(b + 1) % len(blocks)][0]
         assert int(hdr["nbw_next"]) == int(nxt["nbw"]) and np.array_equal(hdr["bw_next"], nxt["bw"])
+        # the slot of the previous block's half-word (the one word asynchronous staging cannot have up to date)
+        prev_hw = (int(blocks[b - 1][0]["v0"]) >> 4) if b > 0 else None
+        want_prev = words.index(prev_hw) + 1 if (prev_hw is not None and prev_hw in words) else 0
+        assert int(hdr["prev_slot"]) == want_prev
+        total_pre = 0
         for i in range(nv):
             u = v0 + i
-            start, end = int(hdr["row"][i]) & 0xFFFF, int(hdr["row"][i]) >> 16
             row = rows[u] if u < n else []
             later = sorted([(j, k) for k, (j, _) in enumerate(row) if j > u])      # stable: ties keep adjacency order
-            earlier = sorted([(j, k) for k, (j, _) in enumerate(row) if j < u])
-            want = [(j, 2.0 * row[k][1]) for j, k in later + earlier]
-            got = [(int(e["j"]), float(e["J2"])) for e in ent[start:end]]
-            assert got == want, f"row {u}: replay order / 2J"
-            assert int(hdr["deg"][i]) == len(row) and (int(hdr["nlater"][i]) & 0xFFF) == len(later)
-            for e in ent[start:end]:
-                j, B = int(e["j"]), int(e["B"])
-                assert (B & 31) == 31 - (j & 31)
-                slot = (B >> 8) & 31
-                assert (slot == 0 and (j >> 5) == own) or (slot > 0 and words[slot - 1] == (j >> 5))
-                assert bool(B & 0x8000) == (v0 <= j < v0 + nv)
+            early = sorted([(j, k) for k, (j, _) in enumerate(row) if j < v0])
+            inblk = sorted([(j, k) for k, (j, _) in enumerate(row) if v0 <= j < u])
+            pre, pad, seq = row_parts(hdr, ent, i)
+            assert [(int(e["B"]) >> 12, float(e["J"])) for e in pre] == [(j, row[k][1]) for j, k in later + early], f"row {u}: pre part"
+            assert [(int(e["B"]) >> 12, float(e["J"])) for e in seq] == [(j, row[k][1]) for j, k in inblk], f"row {u}: seq part"
+            assert all(float(e["J"]) == 0.0 for e in pad) and len(pre) + len(pad) == 4 * (int(hdr["rowa"][i]) & 255)
+            assert int(hdr["rowa"][i]) >> 16 == len(row) and (int(hdr["rowb"][i]) & 0xFFFF) == len(later)
+            for e in list(pre) + list(seq):
+                j, B = int(e["B"]) >> 12, int(e["B"])
+                assert int(e["zero"]) == 0 and (B & 31) == 30 - 2 * (j & 15)
+                slot = (B >> 7) & 31
+                assert (slot == 0 and (j >> 4) == own) or (slot > 0 and words[slot - 1] == (j >> 4))
+            for e in pad:   # zero coupling: any readable slot will do
+                assert int(e["zero"]) == 0 and ((int(e["B"]) >> 7) & 31) == 0
+            total_pre += 4 * (int(hdr["rowa"][i]) & 255)
             if model.groups is not None and u < n and model.groups.grp[u] >= 0:
                 ga = int(hdr["ga"][i])
                 assert (ga & 255) == model.groups.grp[u] and (ga >> 8) == model.groups.coef[u]
             else:
                 assert (int(hdr["ga"][i]) & 255) == 255
+        assert total_pre == int(hdr["seq_off"])
         v += nv
     assert v == npad
 
@@ -127,15 +148,29 @@ def replay_from_slabs(model, rows, blocks, state, betas, spb, seed):
         thr = 44.36142 / beta
         for _ in range(spb):
             for hdr, ent in blocks:
-                for i in range(int(hdr["nv"])):
-                    v = int(hdr["v0"]) + i
+                v0, nv = int(hdr["v0"]), int(hdr["nv"])
+                # batch phase: the pre parts of all rows see the state as of the START of the block
+                Fb, sb = F.copy(), s.copy()
+                part = []
+                for i in range(nv):
+                    pre, pad, _ = row_parts(hdr, ent, i)
+                    acc = f[v0 + i] if v0 + i < n else 0.0
+                    for e in list(pre) + list(pad):
+                        u = int(e["B"]) >> 12
+                        sigma = (2.0 if sb[u] > 0 else -2.0) if Fb[u] else 0.0
+                        acc = acc + float(e["J"]) * sigma
+                    part.append(acc)
+                # sequential phase: in-block earlier neighbours (decided in this block), then the decision
+                for i in range(nv):
+                    v = v0 + i
                     if v >= n:
                         break
-                    start, end = int(hdr["row"][i]) & 0xFFFF, int(hdr["row"][i]) >> 16
-                    for e in ent[start:end]:
-                        u = int(e["j"])
+                    fv = part[i]
+                    for e in row_parts(hdr, ent, i)[2]:
+                        u = int(e["B"]) >> 12
                         if F[u]:
-                            f[v] = f[v] + (float(e["J2"]) if s[u] > 0 else -float(e["J2"]))
+                            fv = fv + float(e["J"]) * (2.0 if s[u] > 0 else -2.0)
+                    f[v] = fv
                     dE = -2.0 * s[v] * f[v]
                     flip = False
                     if not (dE >= thr):
@@ -175,7 +210,7 @@ def test_four_way_model_packs_into_smaller_blocks():
     rows, blocks, uniform = pack(model)
     check_invariants(model, rows, blocks)
     sizes = np.array([int(h["nv"]) for h, _ in blocks])
-    assert not uniform and sizes.min() >= 1 and sizes.mean() >= 4
+    assert sizes.min() >= 1 and sizes.mean() >= 4
 
 
 def test_dense_and_scattered_models_are_rejected(graph256):
