@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "libqanneal.so"
+LIB_PATH = Path(os.environ.get("QA_LIB_PATH", _HERE / "csrc" / "libqanneal.so"))   # QA_LIB_PATH: development builds
 
 QA_OK = 0
 QA_SEED_PER_READ = 0

@@ -1861,7 +1861,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         const int tpp = (reads_per_problem + 31) / 32;
         const int mg = std::max(M->ngroups, 1);
         int nw = ctx->replay_warps;
-        if ((nw != 1 && nw != 2 && nw != 4 && nw != 8 && nw != 16) || nw > RP_MAX_WARPS) {
+        if (nw < 1 || nw > RP_MAX_WARPS) {
             nw = 1;
             while (nw < RP_MAX_WARPS && nw < tpp) nw *= 2;
             while (nw > 1 && rp_smem_bytes(nw, mg, ctx->rp_smem_base) > (size_t)(226 * 1024 / RP_MIN_CTAS - 1024)) nw /= 2;   // RP_MIN_CTAS CTAs per SM
