@@ -46,14 +46,19 @@ constexpr int RP_D = 16;                      // variables per block, at most (=
 constexpr int RP_SLOTS = 32;                  // half-word slots per warp: slot 0 = the block's own half-word
 constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign half-words per block
 constexpr int RP_CAP = 448;                   // entry slots per slab (pre parts in rounds of 4, then the seq parts)
-constexpr int RP_STAGES = 4;      // power of two: stage = g & 3, phase = (g >> 2) & 1 for the running block counter g
+#ifndef RP_STAGES
+#define RP_STAGES 4   // ring stages: stage = g % RP_STAGES, phase = (g / RP_STAGES) & 1 for the running block counter g
+#endif
 #ifndef RP_LA
 #define RP_LA 4     // local fields are loaded this many rows ahead of their use in the batch phase
 #endif
 #ifndef RP_PF_DIST
 #define RP_PF_DIST 32   // L2 run-ahead of the field rows, in variables
 #endif
-constexpr int RP_DIST = 2;        // slabs are requested this many blocks ahead of the first warp that will need them
+#ifndef RP_DIST
+#define RP_DIST 2     // slabs are requested this many blocks ahead of the first warp that will need them (< RP_STAGES)
+#endif
+static_assert(RP_DIST < RP_STAGES, "the ring must hold the block in use and the requested ones");
 constexpr int RP_SF_BYTES = RP_SLOTS * 32 * 4;   // per warp: {S | F << 16}[slot][lane]; 4 KB, aligned to its size
 constexpr int RP_PS_BYTES = RP_D * 32 * 8;       // per warp: partial sums [row][lane] (push phase: the block's fields)
 constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 7;
@@ -193,7 +198,7 @@ __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
         if (old == cur) {
             int b = blk + (int)(cur - c.gb);
             while (b >= c.nblk) b -= c.nblk;
-            const uint32_t st = cur & (RP_STAGES - 1), ph = (cur / RP_STAGES) & 1u;
+            const uint32_t st = cur % RP_STAGES, ph = (cur / RP_STAGES) & 1u;
             mbar_wait(c.empty_s + 8u * st, ph ^ 1u);     // every warp has released the previous use of that stage
             const uint32_t o0 = __ldg(c.off + b), o1 = __ldg(c.off + b + 1);
             const uint32_t bytes = (o1 - o0) * 16u;
@@ -253,7 +258,7 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 
     const uint32_t g_last = c.gb + (uint32_t)nblk - 1u;   // running index of the last block of this pass
     for (int blk = 0; blk < nblk; ++blk) {
-        const uint32_t stage = c.gb & (RP_STAGES - 1), phase = (c.gb / RP_STAGES) & 1u;
+        const uint32_t stage = c.gb % RP_STAGES, phase = (c.gb / RP_STAGES) & 1u;
         if (lane == 0) {
             uint32_t tgt = c.gb + (uint32_t)RP_DIST;
             if (!has_next_pass && (int)(tgt - g_last) > 0) tgt = g_last;
