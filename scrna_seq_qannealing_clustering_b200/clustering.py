@@ -9,9 +9,12 @@ Each builds the reference's model (models.py), hands it to ``sampler`` (default:
 the dimod call the reference makes, and consumes the SampleSet the way the reference does (labels on the graph,
 recursion rules).  ``solver`` / ``dirs`` / ``chain_strength`` are accepted for signature compatibility; QPU-only
 kwargs are forwarded and dropped by the sampler with a warning, as neal would.
+The recursion rules are restated literally in ``bqm_rule`` / ``bqm2_rule`` (ratio test, |e3| <= 0.1 early return with
+one colour, ``min(len) > 5``, labels overwritten after a ``conf`` recursion, ``100 - color`` labels of ``clustering_bqm_2``).
 Deviations, all deliberate: the reference's recursive calls omit ``chain_strength`` (TypeError on first recursion,
 SURVEY.md 3.1) -- here the argument is passed; its ``conf`` rule reads ``record.energy[0]/[3]`` assuming an
-energy-sorted record -- here the SampleSet is requested sorted.
+energy-sorted record -- here the SampleSet is requested sorted; the functions return the level's SampleSet on every path
+(the reference returns None on most).
 """
 from __future__ import annotations
 
@@ -54,26 +57,62 @@ def _label(G, nodes, label, value):
         G.nodes[i][label] = value
 
 
-def _recurse(fn, G, S0, S1, iteration, response, terminate_on, size_limit, iter_limit, color, args, kwargs):
-    """Termination rules of BQM_clustering.py:113-203 (min_size / conf / once / iter_limit)."""
-    label = "label" + str(iteration)
-    go = False
+def bqm_rule(terminate_on, n0, n1, energies, iteration, size_limit, iter_limit):
+    """The reference's termination rules for ``clustering_bqm``, restated literally (BQM_clustering.py:113-203).
+
+    ``energies`` is the energy-sorted record (``response.record.energy``).  Returns ``(recurse, labels)`` where ``labels``
+    says what the reference writes into ``G.nodes[.]['label<iteration>']`` at this level: ``'split'`` (one random colour
+    per half), ``'single'`` (one random colour for every node) or ``None`` (nothing written).  In the ``conf`` branch the
+    reference labels the halves, recurses, and then overwrites the level's label with a single colour: the net effect on
+    this level's label is ``'single'``.
+    """
+    if terminate_on == "min_size":                                   # :113-131
+        go = n0 > size_limit and n1 > size_limit and iteration < iter_limit
+        return go, ("split" if go else None)
+    if terminate_on == "conf":                                       # :133-178
+        if len(energies) > 3:
+            e0, e3 = float(energies[0]), float(energies[3])
+            if not (e3 > 0.1 or e3 < -0.1):                          # "3rd lowest energy too close to zero"
+                return False, "single"
+            ratio = e0 / e3
+            go = ratio > 1.5 and min(n0, n1) > 5 and iteration < iter_limit
+            return go, "single"
+        if min(n0, n1) > 5 and iteration < iter_limit:
+            return True, "split"
+        return False, "single"
+    if terminate_on == "once":                                       # :180-187
+        return False, "split"
+    if terminate_on == "iter_limit":                                 # :189-201
+        go = iteration < iter_limit
+        return go, ("split" if go else None)
+    return False, None
+
+
+def bqm2_rule(terminate_on, n0, n1, energies, size_limit):
+    """``clustering_bqm_2``'s rules (BQM_clustering.py:302-350): ``'color'`` = the deterministic ``100 - color`` /
+    ``color - 100`` labels of its ``min_size`` branch.  (The reference indexes ``energy[3]`` unconditionally in the ``conf``
+    branch; fewer than four reads end the recursion here instead of raising IndexError.)"""
     if terminate_on == "min_size":
-        go = len(S0) > size_limit and len(S1) > size_limit and iteration < iter_limit
-    elif terminate_on == "conf":
-        e = response.record.energy
-        conf = abs(e[0] - e[min(3, len(e) - 1)]) if len(e) > 1 else 0.0
-        go = len(S0) > size_limit and len(S1) > size_limit and iteration < iter_limit and (conf > 0 or len(e) < 4)
-    elif terminate_on == "iter_limit":
-        go = iteration < iter_limit and len(S0) > 1 and len(S1) > 1
-    _label(G, S0, label, random.randint(0, 100))
-    _label(G, S1, label, random.randint(120, 220))
-    if terminate_on == "once" or not go:
-        return
-    fn(G.subgraph(S0), iteration + 1, *args, color=color + 20, terminate_on=terminate_on, size_limit=size_limit,
-       iter_limit=iter_limit, **kwargs)
-    fn(G.subgraph(S1), iteration + 1, *args, color=color + 20, terminate_on=terminate_on, size_limit=size_limit,
-       iter_limit=iter_limit, **kwargs)
+        return (n0 > size_limit and n1 > size_limit), "color"
+    if terminate_on == "conf":
+        if len(energies) < 4:
+            return False, None
+        go = abs(float(energies[0]) - float(energies[3])) > 10 and min(n0, n1) > 5
+        return go, ("split" if go else None)
+    if terminate_on == "once":
+        return False, "split"
+    return False, None
+
+
+def _write_labels(G, S0, S1, label, how, color=0):
+    if how == "split":
+        _label(G, S0, label, random.randint(0, 100))
+        _label(G, S1, label, random.randint(120, 220))
+    elif how == "single":
+        _label(G, list(G.nodes), label, random.randint(0, 100))
+    elif how == "color":
+        _label(G, S0, label, 100 - color)
+        _label(G, S1, label, color - 100)
 
 
 def clustering_bqm(G, iteration, dirs, solver, gamma_factor, color=0, terminate_on="once", size_limit=40, iter_limit=2,
@@ -84,21 +123,34 @@ def clustering_bqm(G, iteration, dirs, solver, gamma_factor, color=0, terminate_
     response = _sample(_sampler(sampler), model, {"label": str(dirs.get("name", "")) + "_" + str(solver),
                                                    "chain_strength": chain_strength}, sa_kwargs)
     S0, S1 = _split(G, response)
-    _recurse(clustering_bqm, G, S0, S1, iteration, response, terminate_on, size_limit, iter_limit, color,
-             (dirs, solver, gamma_factor), dict(chain_strength=chain_strength, sampler=sampler, structured=structured, **sa_kwargs))
+    go, how = bqm_rule(terminate_on, len(S0), len(S1), response.record.energy, iteration, size_limit, iter_limit)
+    label = "label" + str(iteration)
+    if go:
+        _write_labels(G, S0, S1, label, "split")     # the reference labels the halves before it recurses
+        for part in (S0, S1):
+            clustering_bqm(G.subgraph(part), iteration + 1, dirs, solver, gamma_factor, color=color + 20, terminate_on=terminate_on,
+                           size_limit=size_limit, iter_limit=iter_limit, chain_strength=chain_strength, sampler=sampler,
+                           structured=structured, **sa_kwargs)
+    if how is not None and not (go and how == "split"):
+        _write_labels(G, S0, S1, label, how)
     return response
 
 
 def clustering_bqm_2(G, iteration, dirs, solver, gamma_factor, color=0, terminate_on="once", size_limit=40, k=1,
-                     chain_strength=None, sampler=None, iter_limit=2, **sa_kwargs):
-    """2-way cut + linear gamma (BQM_clustering.py:206-350)."""
+                     chain_strength=None, sampler=None, **sa_kwargs):
+    """2-way cut + linear gamma with the reference's recursion (BQM_clustering.py:206-350)."""
+    if terminate_on not in ("min_size", "conf", "once"):
+        raise NotImplementedError(f"clustering_bqm_2 has no terminate_on={terminate_on!r} branch (BQM_clustering.py:302-350)")
     model = models.cut_linear_model(G, gamma_factor, k)
     sa_kwargs.setdefault("num_reads", 5000)  # BQM_clustering.py:240
     response = _sample(_sampler(sampler), model, {"label": str(dirs.get("name", "")) + "_" + str(solver)}, sa_kwargs)
     S0, S1 = _split(G, response)
-    label = "label" + str(iteration)
-    _label(G, S0, label, random.randint(0, 100))
-    _label(G, S1, label, random.randint(120, 220))
+    go, how = bqm2_rule(terminate_on, len(S0), len(S1), response.record.energy, size_limit)
+    _write_labels(G, S0, S1, "label" + str(iteration), how, color)
+    if go:
+        for part in (S0, S1):
+            clustering_bqm_2(G.subgraph(part), iteration + 1, dirs, solver, gamma_factor, color=color + 20, terminate_on=terminate_on,
+                             size_limit=size_limit, k=k, chain_strength=chain_strength, sampler=sampler, **sa_kwargs)
     return response
 
 

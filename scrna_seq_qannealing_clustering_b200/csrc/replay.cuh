@@ -45,7 +45,9 @@
 constexpr int RP_D = 16;                      // variables per block, at most (= one half-word of spins)
 constexpr int RP_SLOTS = 32;                  // half-word slots per warp: slot 0 = the block's own half-word
 constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign half-words per block
-constexpr int RP_CAP = 448;                   // entry slots per slab (pre parts in rounds of 4, then the seq parts)
+#ifndef RP_CAP
+#define RP_CAP 448     // entry slots per slab (pre parts in rounds of 4, then the seq parts)
+#endif
 #ifndef RP_STAGES
 #define RP_STAGES 4   // ring stages: stage = g % RP_STAGES, phase = (g / RP_STAGES) & 1 for the running block counter g
 #endif
@@ -189,17 +191,20 @@ struct RpCtx {
     int n, nblk, npad;
 };
 
-// lane 0 of any warp: request every slab up to running index `tgt` that nobody has requested yet.  `blk` is the block the
-// calling warp is about to consume (running index c.gb); slabs follow the cyclic block order of the passes.
+// lane 0 of any warp: request every slab up to running index `tgt` that nobody has requested yet and whose ring stage is
+// free.  `blk` is the block the calling warp is about to consume (running index c.gb); slabs follow the cyclic block order
+// of the passes.  NON-BLOCKING: a stage still in use by a slower warp ends the attempt (a warp that blocked here would couple
+// the fastest warp of the CTA to the slowest one: measured -8 % with one block of slack less); the request is retried by
+// whoever comes next, and by any warp that finds its own slab missing (rp_pass).
 __device__ __forceinline__ void rp_request(RpCtx &c, uint32_t tgt, int blk) {
     unsigned cur = *reinterpret_cast<volatile unsigned *>(c.issued);
     while ((int)(tgt - cur) >= 0) {
+        const uint32_t st = cur % RP_STAGES, ph = (cur / RP_STAGES) & 1u;
+        if (!mbar_try_wait(c.empty_s + 8u * st, ph ^ 1u)) return;   // not every warp has released the previous use of that stage
         const unsigned old = atomicCAS(c.issued, cur, cur + 1u);
         if (old == cur) {
             int b = blk + (int)(cur - c.gb);
             while (b >= c.nblk) b -= c.nblk;
-            const uint32_t st = cur % RP_STAGES, ph = (cur / RP_STAGES) & 1u;
-            mbar_wait(c.empty_s + 8u * st, ph ^ 1u);     // every warp has released the previous use of that stage
             const uint32_t o0 = __ldg(c.off + b), o1 = __ldg(c.off + b + 1);
             const uint32_t bytes = (o1 - o0) * 16u;
             mbar_expect_tx(c.full_s + 8u * st, bytes);
@@ -265,7 +270,9 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
             rp_request(c, tgt, blk);
         }
         __syncwarp();
-        mbar_wait(c.full_s + 8u * stage, phase);
+        while (!mbar_try_wait(c.full_s + 8u * stage, phase)) {   // usually there; else make sure somebody has asked for it
+            if (lane == 0) rp_request(c, c.gb, blk);
+        }
         const uint32_t hdr = c.stage_s + stage * (uint32_t)RP_STAGE_BYTES;   // shared address of the slab
         const uint32_t ent = hdr + (uint32_t)sizeof(RpHdr);
         const int v0 = (int)lds_u32(hdr + RP_H_V0);

@@ -60,3 +60,80 @@ def test_size_limit_and_iteration_limit_stop_the_recursion():
     labels, levels, _ = clustering.recursive_bipartition_batched(G, 0.05, size_limit=5, iter_limit=0, num_reads=32, num_sweeps=100,
                                                                  seed=1, context=ctx)
     assert ctx.calls == 1                                               # iteration limit reached at the first level
+
+
+# ---- the reference's termination rules, restated literally (the default `conf` path must match) ----------
+class StubSampler:
+    """Returns a crafted energy-sorted SampleSet: the first half of the nodes in S1, energies as given per call."""
+
+    def __init__(self, energies_per_call):
+        self.energies = list(energies_per_call)
+        self.calls = []
+
+    def sample(self, model, **kw):
+        from scrna_seq_qannealing_clustering_b200.sampleset import SampleSet
+        labels = list(model.labels)
+        n = len(labels)
+        self.calls.append(labels)
+        e = self.energies.pop(0) if self.energies else [-1.0, -1.0, -1.0, -1.0]
+        rows = np.zeros((len(e), n), dtype=np.int8)
+        rows[:, : n // 2] = 1
+        return SampleSet.from_samples((rows, labels), energy=np.asarray(e, dtype=float), vartype="BINARY")
+
+
+def _path_graph(n):
+    import networkx as nx
+    G = nx.Graph()
+    G.add_nodes_from(str(i) for i in range(n))
+    for i in range(n - 1):
+        G.add_edge(str(i), str(i + 1), weight=0.5)
+    return G
+
+
+def test_bqm_rule_matches_the_reference_branches():
+    r = clustering.bqm_rule
+    # conf, > 3 energies: ratio e0/e3 > 1.5, both halves > 5, iteration < iter_limit -> recurse; label ends as one colour
+    assert r("conf", 10, 10, [-30.0, -29.0, -28.0, -15.0], 0, 40, 2) == (True, "single")
+    assert r("conf", 10, 10, [-30.0, -29.0, -28.0, -25.0], 0, 40, 2) == (False, "single")      # ratio 1.2
+    assert r("conf", 10, 5, [-30.0, -29.0, -28.0, -15.0], 0, 40, 2) == (False, "single")       # min(len) > 5 fails
+    assert r("conf", 10, 10, [-30.0, -29.0, -28.0, -15.0], 2, 40, 2) == (False, "single")      # iteration limit
+    assert r("conf", 10, 10, [-30.0, -29.0, -28.0, 0.05], 0, 40, 2) == (False, "single")       # |e3| <= 0.1: early return
+    assert r("conf", 10, 10, [3.0, 2.0, 1.5, 1.0], 0, 40, 2) == (True, "single")               # positive energies: ratio 3
+    # conf, <= 3 energies: size rule alone
+    assert r("conf", 10, 10, [-3.0, -2.0], 0, 40, 2) == (True, "split")
+    assert r("conf", 10, 4, [-3.0, -2.0], 0, 40, 2) == (False, "single")
+    # min_size writes nothing when it stops; iter_limit ignores the sizes
+    assert r("min_size", 41, 41, [], 0, 40, 2) == (True, "split") and r("min_size", 41, 40, [], 0, 40, 2) == (False, None)
+    assert r("iter_limit", 1, 0, [], 1, 40, 2) == (True, "split") and r("iter_limit", 50, 50, [], 2, 40, 2) == (False, None)
+    assert r("once", 50, 50, [], 0, 40, 2) == (False, "split")
+    r2 = clustering.bqm2_rule
+    assert r2("min_size", 41, 41, [], 40) == (True, "color") and r2("min_size", 41, 40, [], 40) == (False, "color")
+    assert r2("conf", 10, 10, [-30.0, -29.0, -28.0, -15.0], 40) == (True, "split")
+    assert r2("conf", 10, 10, [-30.0, -29.0, -28.0, -25.0], 40) == (False, None)              # difference <= 10
+
+
+def test_conf_recursion_tree_and_labels_follow_the_reference():
+    G = _path_graph(48)
+    # level 0: recurse (ratio 2); the two children: one stops on the ratio, one on |e3| <= 0.1
+    stub = StubSampler([[-30.0, -29.0, -28.0, -15.0], [-8.0, -7.5, -7.2, -7.0], [-8.0, -7.5, -7.2, 0.0]])
+    clustering.clustering_bqm(G, 0, {"name": "t"}, "stub", 0.05, terminate_on="conf", size_limit=40, iter_limit=2, sampler=stub)
+    assert [len(c) for c in stub.calls] == [48, 24, 24]
+    assert len({G.nodes[n]["label0"] for n in G.nodes}) == 1            # overwritten with one colour after the recursion
+    assert all("label1" in G.nodes[n] for n in G.nodes) and all("label2" not in G.nodes[n] for n in G.nodes)
+    # the default size_limit plays no role in `conf`: halves of 24 > 5 recursed although size_limit = 40
+
+
+def test_min_size_and_bqm2_recursion():
+    G = _path_graph(40)
+    stub = StubSampler([])
+    clustering.clustering_bqm(G, 0, {"name": "t"}, "stub", 0.05, terminate_on="min_size", size_limit=9, iter_limit=5, sampler=stub)
+    assert [len(c) for c in stub.calls] == [40, 20, 10, 10, 20, 10, 10]       # depth-first: halves of 5 are not > 9... 10 > 9 recursed
+    G = _path_graph(40)
+    stub = StubSampler([])
+    clustering.clustering_bqm_2(G, 0, {"name": "t"}, "stub", 0.01, color=0, terminate_on="min_size", size_limit=9, k=1, sampler=stub)
+    assert [len(c) for c in stub.calls] == [40, 20, 10, 10, 20, 10, 10]
+    assert {G.nodes[n]["label0"] for n in G.nodes} == {100, -100}             # 100 - color / color - 100
+    assert {G.nodes[n]["label1"] for n in G.nodes} == {80, -80}
+    import pytest
+    with pytest.raises(NotImplementedError):
+        clustering.clustering_bqm_2(G, 0, {"name": "t"}, "stub", 0.01, terminate_on="iter_limit", sampler=stub)
