@@ -181,10 +181,14 @@ int qa_sort_reads(qa_ctx *ctx, int32_t num_reads, const double *energies, int32_
 int qa_gather_samples(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *states, int32_t k, const int32_t *order,
                       int8_t *samples_out);
 /* one-hot decode: variable (cell i, case c) = states[read][i*K + c] (stride >= cells*K bytes per read; on_value = +1 for
- * spins, 1 for binaries).  labels_out[read][cell] = case or -1 when the cell is not one-hot;
- * violations_out[read] = {cells that are not one-hot, cases with fewer than min_size cells} */
+ * spins, 1 for binaries).  labels_out[read][cell] = case or -1 when the cell is not one-hot (labels_out may be NULL: only
+ * the counts are wanted); violations_out[read] = {cells that are not one-hot, cases with fewer than min_size cells} */
 int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int32_t num_reads, const int8_t *states,
                      int32_t on_value, int32_t min_size, int32_t *labels_out, int32_t *violations_out);
+
+/* Lowest value and its first index (SampleSet.first; the per-rank half of the multi-GPU best-sample gather):
+ * warp-shuffle min-reduction, ties to the lower index.  values: host or device pointer. */
+int qa_argmin(qa_ctx *ctx, int64_t count, const double *values, double *best_value, int64_t *best_index);
 
 /* Test hook, host only (no device needed): the coupling slabs the replay kernel would get for a CSR in host memory
  * (adjacency order).  Returns 1 when the model fits the slab format, 0 when it does not, < 0 on error. */

@@ -101,6 +101,7 @@ SIGNATURES = {
     "qa_build_dqm_onehot": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _i32, C.POINTER(_p), C.POINTER(C.c_double)]),
     "qa_build_cqm_penalty": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _i32, C.c_double, C.c_double, C.POINTER(_p), C.POINTER(C.c_double)]),
     "qa_energy_argmin": (C.c_int, [_p, _p, _i32, _p, _p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(QAStats)]),
+    "qa_argmin": (C.c_int, [_p, _i64, _p, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "qa_debug_pack_slabs": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "qa_sort_reads": (C.c_int, [_p, _i32, _p, _p]),
     "qa_gather_samples": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p]),

@@ -44,7 +44,7 @@ __global__ void k_decode_onehot(int32_t cells, int32_t K, int64_t stride, int32_
     } else {
         atomicAdd(sizes + (int64_t)r * K + lab, 1);
     }
-    labels[t] = lab;
+    if (labels) labels[t] = lab;
 }
 
 __global__ void k_count_small_clusters(int32_t reads, int32_t K, int32_t min_size, const int32_t *sizes, int32_t *violations) {
@@ -137,26 +137,52 @@ int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int3
     if (!ctx) return fail(QA_ERR_ARG, "null context");
     if (cells < 0 || K < 1 || num_reads < 0 || stride < (int64_t)cells * K) return fail(QA_ERR_ARG, "bad one-hot geometry");
     if (num_reads == 0 || cells == 0) return QA_OK;
-    if (!states || !labels_out || !violations_out) return fail(QA_ERR_ARG, "null states / labels / violations");
+    if (!states || !violations_out) return fail(QA_ERR_ARG, "null states / violations");   // labels_out may be NULL: counts only
     QA_CUDA(cudaSetDevice(ctx->device));
     const void *d_states = nullptr;
     int rc = stage_in(ctx, ctx->states, states, (size_t)num_reads * stride, &d_states);
     if (rc) return rc;
-    const size_t lb = (size_t)num_reads * cells * sizeof(int32_t), sb = (size_t)num_reads * K * sizeof(int32_t),
+    const size_t lb = labels_out ? (size_t)num_reads * cells * sizeof(int32_t) : 0, sb = (size_t)num_reads * K * sizeof(int32_t),
                  vb = (size_t)num_reads * 2 * sizeof(int32_t);
     rc = ensure(ctx->misc, lb + sb + vb + 64);
     if (rc) return rc;
-    int32_t *d_lab = (int32_t *)ctx->misc.p, *d_sizes = d_lab + (size_t)num_reads * cells, *d_viol = d_sizes + (size_t)num_reads * K;
+    int32_t *d_lab = (int32_t *)ctx->misc.p, *d_sizes = d_lab + lb / sizeof(int32_t), *d_viol = d_sizes + (size_t)num_reads * K;
     QA_CUDA(cudaMemsetAsync(d_sizes, 0, sb + vb, ctx->stream));
     const int64_t total = (int64_t)num_reads * cells;
     k_decode_onehot<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(cells, K, stride, num_reads, (const int8_t *)d_states,
-                                                                               on_value, d_lab, d_sizes, d_viol);
+                                                                               on_value, labels_out ? d_lab : nullptr, d_sizes, d_viol);
     k_count_small_clusters<<<(num_reads + 255) / 256, 256, 0, ctx->stream>>>(num_reads, K, min_size, d_sizes, d_viol);
     QA_CUDA(cudaGetLastError());
     ctx->launches += 2;
-    QA_CUDA(cudaMemcpyAsync(labels_out, d_lab, lb, cudaMemcpyDefault, ctx->stream));
+    if (labels_out) QA_CUDA(cudaMemcpyAsync(labels_out, d_lab, lb, cudaMemcpyDefault, ctx->stream));
     QA_CUDA(cudaMemcpyAsync(violations_out, d_viol, vb, cudaMemcpyDefault, ctx->stream));
     QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_argmin(qa_ctx *ctx, int64_t count, const double *values, double *best_value, int64_t *best_index) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (count < 0) return fail(QA_ERR_ARG, "negative count");
+    if (count == 0) {
+        if (best_value) *best_value = INFINITY;
+        if (best_index) *best_index = -1;
+        return QA_OK;
+    }
+    if (!values) return fail(QA_ERR_ARG, "null values");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const void *d_v = nullptr;
+    int rc = stage_in(ctx, ctx->energies, values, (size_t)count * sizeof(double), &d_v);
+    if (rc) return rc;
+    k_argmin<<<1, 1024, 0, ctx->stream>>>((const double *)d_v, count, ctx->d_best_e, ctx->d_best_i);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches++;
+    double be = 0;
+    long long bi = 0;
+    QA_CUDA(cudaMemcpyAsync(&be, ctx->d_best_e, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(&bi, ctx->d_best_i, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (best_value) *best_value = be;
+    if (best_index) *best_index = bi;
     return QA_OK;
 }
 

@@ -91,17 +91,27 @@ class Context:
         check(_lib.load().qa_gather_samples(self._h, n, num_reads, ptr(states), len(order), ptr(order), ptr(out)))
         return out
 
-    def decode_onehot(self, states, cells: int, num_cases: int, on_value: int = 1, min_size: int = 0):
+    def decode_onehot(self, states, cells: int, num_cases: int, on_value: int = 1, min_size: int = 0, want_labels: bool = True):
         """Labels of a DQM / CQM sample matrix: ``labels[read][cell]`` (-1: the cell is not one-hot) and per read the number of
-        cells that are not one-hot and of cases with fewer than ``min_size`` cells (CQM_clustering.py:44-48)."""
+        cells that are not one-hot and of cases with fewer than ``min_size`` cells (CQM_clustering.py:44-48).
+        ``want_labels=False`` returns ``(None, violations)``: only the 8 bytes per read leave the device."""
         num_reads, stride = int(states.shape[0]), int(states.shape[1])
         if not _is_tensor(states):
             states = np.ascontiguousarray(states, dtype=np.int8)
-        labels = np.empty((num_reads, cells), dtype=np.int32)
+        labels = np.empty((num_reads, cells), dtype=np.int32) if want_labels else None
         violations = np.empty((num_reads, 2), dtype=np.int32)
         check(_lib.load().qa_decode_onehot(self._h, int(cells), int(num_cases), stride, num_reads, ptr(states), int(on_value),
                                            int(min_size), ptr(labels), ptr(violations)))
         return labels, violations
+
+    def argmin(self, values):
+        """(lowest value, its first index) by the warp-shuffle reduction kernel; ``values`` numpy or a CUDA tensor (fp64)."""
+        count = int(values.shape[0])
+        if not _is_tensor(values):
+            values = np.ascontiguousarray(values, dtype=np.float64)
+        bv, bi = C.c_double(), C.c_int64()
+        check(_lib.load().qa_argmin(self._h, count, ptr(values), C.byref(bv), C.byref(bi)))
+        return float(bv.value), int(bi.value)
 
     # -- model construction on the device (qa_build_*): graph = (n, eu, ev, w) in G.edges order ---
     def _graph_args(self, graph):
