@@ -673,13 +673,16 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
     c.SF = reinterpret_cast<uint32_t *>(P.sf_scratch) + slot * P.sf_stride + lane;
     int acc_par = 0;
 
+    bool first_item = true;   // neal polls its interrupt callback BETWEEN reads: every CTA completes the first group it takes
     for (;;) {
-        if (P.interrupt_flag != nullptr && threadIdx.x == 0) {   // host-mapped flag set by the caller's interrupt callback
-            if (*reinterpret_cast<const volatile int *>(P.interrupt_flag) != 0) *item_sh = (long long)P.total_items;
-            else *item_sh = (long long)atomicAdd(P.counter, 1ull);
-        } else if (threadIdx.x == 0) {
-            *item_sh = (long long)atomicAdd(P.counter, 1ull);
+        if (threadIdx.x == 0) {
+            // host-mapped flag raised by the caller's interrupt callback: stop pulling work (without counting the pull)
+            if (P.interrupt_flag != nullptr && !first_item && *reinterpret_cast<const volatile int *>(P.interrupt_flag) != 0)
+                *item_sh = (long long)P.total_items;
+            else
+                *item_sh = (long long)atomicAdd(P.counter, 1ull);
         }
+        first_item = false;
         __syncthreads();
         const int64_t item = *item_sh;
         __syncthreads();

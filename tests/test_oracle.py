@@ -189,3 +189,100 @@ def test_input_validation():
         oracle.sample_ising(h, [1], [1], [1.0], np.ones((1, 3), dtype=np.int8), [1.0], 1, [1])
     with pytest.raises(RuntimeError):
         oracle.sample_ising(h, [1], [0], [1.0], np.zeros((1, 3), dtype=np.int8), [1.0], 1, [1])
+
+
+# ---- the rank-1 GROUP extension, checked by something other than oracle/cpu_sa_ref.cpp ------------------------
+def py_anneal_groups_checked(model, state, betas, spb, seed, tol=1e-9):
+    """Independent restatement of the structured loop: neal's sweep on the explicit couplers, plus for every variable in a
+    group the lazily evaluated flip cost lambda * a * (a - s (M + kappa)) with integer M.  At EVERY attempt the float flip
+    cost is also compared with the EXACT flip cost of the materialised energy function
+        E(s) = sum h s + sum J s s + sum_g lambda_g / 4 (sum_{v in g} a_v s_v + kappa_g)^2
+    evaluated in rational arithmetic (fractions.Fraction), and the decision taken is required to be the decision the exact
+    value implies unless the margin is inside `tol` (relative)."""
+    from fractions import Fraction as Fr
+    h, starts, ends, w = model.h.tolist(), model.starts.tolist(), model.ends.tolist(), model.weights.tolist()
+    grp, coef, lam, kap = (np.asarray(a).tolist() for a in model.groups.astuple())
+    n = len(h)
+    adj = [[] for _ in range(n)]
+    for u, v, x in zip(starts, ends, w):
+        adj[u].append((v, x))
+        adj[v].append((u, x))
+    s = [int(x) for x in state]
+    M = [0] * len(lam)
+    for v in range(n):
+        if grp[v] >= 0:
+            M[grp[v]] += coef[v] * s[v]
+    dE = []
+    for v in range(n):
+        e = h[v]
+        for j, x in adj[v]:
+            e += s[j] * x
+        dE.append(-2 * s[v] * e)
+
+    def exact_flip_cost(v):
+        f = Fr(h[v]) + sum(Fr(x) * s[j] for j, x in adj[v])
+        d = -2 * s[v] * f
+        g = grp[v]
+        if g >= 0:
+            t = M[g] + kap[g]
+            d += Fr(lam[g]) * (Fr((t - 2 * coef[v] * s[v]) ** 2) - Fr(t ** 2)) / 4
+        return d
+
+    rng = py_rng(seed)
+    checked = 0
+    for beta in betas:
+        thr = 44.36142 / beta
+        for _ in range(spb):
+            for v in range(n):
+                d = dE[v]
+                g = grp[v]
+                if g >= 0:
+                    a = coef[v]
+                    d = d + lam[g] * float(a * (a - s[v] * (M[g] + kap[g])))
+                ex = exact_flip_cost(v)
+                scale = max(1.0, abs(float(ex)), max(abs(x) for _, x in adj[v]) if adj[v] else 0.0)
+                assert abs(d - float(ex)) <= 1e-9 * scale * max(1, len(adj[v])), (v, d, float(ex))
+                checked += 1
+                if d >= thr:
+                    assert float(ex) >= thr * (1 - tol)
+                    continue
+                flip = False
+                if d <= 0.0:
+                    assert float(ex) <= tol * scale
+                    flip = True
+                elif math.exp(-d * beta) * 18446744073709551616.0 > float(next(rng)):
+                    flip = True
+                if flip:
+                    mult = 4 * s[v]
+                    for j, x in adj[v]:
+                        dE[j] += mult * x * s[j]
+                    if g >= 0:
+                        M[g] -= 2 * coef[v] * s[v]
+                    s[v] *= -1
+                    dE[v] *= -1
+    return s, checked
+
+
+@pytest.mark.parametrize("kind", ["cut_balance", "cqm", "dqm"])
+def test_group_extension_against_an_independent_exact_restatement(kind):
+    g = snn.synthetic_snn(24 if kind != "cut_balance" else 40, k=4, seed=2)[0]
+    if kind == "cut_balance":
+        m = models.cut_balance_model(g, 0.05, k=8.0, structured=True)
+        br = (0.02, 6.0)
+    elif kind == "cqm":
+        m = models.cqm_model(g, 3, min_size=4)
+        br = (0.02, 4.0)
+    else:
+        m = models.dqm_model(g, 3, 0.005, semantics="intended")
+        br = (0.02, 6.0)
+    assert m.groups is not None
+    betas = np.geomspace(br[0], br[1], 25)
+    R = 2
+    init = schedule.random_spin_states(R, m.num_variables, 4)
+    seeds = schedule.per_read_seeds(9, R)
+    ref = init.copy()
+    oracle.sample_ising(m.h, m.starts, m.ends, m.weights, ref, betas, 1, seeds, groups=m.groups.astuple())
+    for r in range(R):
+        s_py, checked = py_anneal_groups_checked(m, init[r], betas.tolist(), 1, int(seeds[r]))
+        assert checked == m.num_variables * len(betas)
+        assert ref[r].tolist() == s_py, "the C++ oracle's structured run differs from the independent restatement"

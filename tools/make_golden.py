@@ -16,6 +16,7 @@ import contextlib
 import io
 import json
 import math
+import os
 import sys
 import types
 from pathlib import Path
@@ -25,7 +26,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 REF = Path("/root/reference")
-OUT = ROOT / "tests" / "golden"
+OUT = Path(os.environ["QA_GOLDEN_OUT"]) if os.environ.get("QA_GOLDEN_OUT") else ROOT / "tests" / "golden"
 sys.path.insert(0, str(ROOT))
 
 GRAPHS = ["noisy_circles", "noisy_moons", "varied", "aniso", "blobs", "no_structure"]
@@ -94,8 +95,100 @@ class _RecDQM:
             blk[(cu, cv) if key == (u, v) else (cv, cu)] = float(b)
 
 
+class _Sym:
+    """Dumb stand-in for dimod's symbolic binary expressions (dimod.Binary and the QuadraticModel arithmetic that
+    CQM_clustering.py:30-48 uses): linear / quadratic coefficient dicts in insertion order.  Deliberately independent of the
+    product's cqm.py, so that the CQM fixture is not checked against the code that produced it."""
+
+    def __init__(self, linear=None, quadratic=None, offset=0.0):
+        self.linear = dict(linear or {})
+        self.quadratic = dict(quadratic or {})
+        self.offset = float(offset)
+
+    @staticmethod
+    def _of(x):
+        return x if isinstance(x, _Sym) else _Sym(offset=float(x))
+
+    def __add__(self, other):
+        o = _Sym._of(other)
+        r = _Sym(self.linear, self.quadratic, self.offset + o.offset)
+        for k, b in o.linear.items():
+            r.linear[k] = r.linear.get(k, 0.0) + b
+        for (a, c), b in o.quadratic.items():
+            key = (a, c) if (a, c) in r.quadratic or (c, a) not in r.quadratic else (c, a)
+            r.quadratic[key] = r.quadratic.get(key, 0.0) + b
+        return r
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return _Sym({k: -b for k, b in self.linear.items()}, {k: -b for k, b in self.quadratic.items()}, -self.offset)
+
+    def __sub__(self, other):
+        return self + (-_Sym._of(other))
+
+    def __mul__(self, other):
+        if not isinstance(other, _Sym):
+            c = float(other)
+            return _Sym({k: c * b for k, b in self.linear.items()}, {k: c * b for k, b in self.quadratic.items()}, c * self.offset)
+        if self.quadratic or other.quadratic:
+            raise ValueError("degree > 2")
+        r = _Sym(offset=self.offset * other.offset)
+        for k, b in self.linear.items():
+            if other.offset:
+                r.linear[k] = r.linear.get(k, 0.0) + b * other.offset
+        for k, b in other.linear.items():
+            if self.offset:
+                r.linear[k] = r.linear.get(k, 0.0) + b * self.offset
+        for ka, ba in self.linear.items():
+            for kb, bb in other.linear.items():
+                if ka == kb:      # x * x = x for a binary variable
+                    r.linear[ka] = r.linear.get(ka, 0.0) + ba * bb
+                else:
+                    key = (ka, kb) if (kb, ka) not in r.quadratic else (kb, ka)
+                    r.quadratic[key] = r.quadratic.get(key, 0.0) + ba * bb
+        return r
+
+    __rmul__ = __mul__
+
+    def __ge__(self, rhs):
+        return ("ge", self, float(rhs))
+
+    def __le__(self, rhs):
+        return ("le", self, float(rhs))
+
+    def __eq__(self, rhs):   # noqa: PLW1641  (recorder objects are never hashed)
+        return ("eq", self, float(rhs))
+
+    __hash__ = None
+
+
+def _sym_binary(label):
+    return _Sym({label: 1.0})
+
+
+class _RecCQM:
+    """Records ConstrainedQuadraticModel calls: add_discrete / set_objective / add_constraint (CQM_clustering.py:30-48)."""
+
+    def __init__(self):
+        self.discrete = {}
+        self.objective = None
+        self.constraints = {}
+
+    def add_discrete(self, variables, label=None):
+        self.discrete[label] = list(variables)
+        return label
+
+    def set_objective(self, expr):
+        self.objective = _Sym._of(expr)
+
+    def add_constraint(self, comparison, label=None):
+        sense, lhs, rhs = comparison
+        self.constraints[label] = {"sense": {"ge": ">=", "le": "<=", "eq": "=="}[sense], "lhs": lhs, "rhs": rhs}
+        return label
+
+
 def install_stubs():
-    from scrna_seq_qannealing_clustering_b200 import cqm as our_cqm  # expression algebra only (dimod.Binary stand-in)
 
     def mod(name, **attrs):
         m = types.ModuleType(name)
@@ -104,7 +197,7 @@ def install_stubs():
         return m
 
     dimod = mod("dimod", BinaryQuadraticModel=_RecBQM, DiscreteQuadraticModel=_RecDQM,
-                ConstrainedQuadraticModel=our_cqm.ConstrainedQuadraticModel, Binary=our_cqm.Binary)
+                ConstrainedQuadraticModel=_RecCQM, Binary=_sym_binary)
     mod("hybrid", KerberosSampler=_CaptureSampler)
     dw = mod("dwave")
     dw.inspector = mod("dwave.inspector", show=lambda *a, **k: None)
@@ -216,9 +309,9 @@ def main():
         "qq": np.array([c.objective.quadratic[k] for k in qk], dtype=np.float64),
         "offset": np.array([c.objective.offset]),
         "discrete": np.array([[var_pos[v] for v in grp] for grp in c.discrete.values()], dtype=np.int32),
-        "size_rhs": np.array([-con.lhs.offset for con in c.constraints.values()], dtype=np.float64),
-        "size_vars": np.array([[var_pos[v] for v in con.lhs.linear] for con in c.constraints.values()], dtype=np.int32),
-        "size_sense_ge": np.array([con.sense == ">=" for con in c.constraints.values()]),
+        "size_rhs": np.array([con["rhs"] - con["lhs"].offset for con in c.constraints.values()], dtype=np.float64),
+        "size_vars": np.array([[var_pos[v] for v in con["lhs"].linear] for con in c.constraints.values()], dtype=np.int32),
+        "size_sense_ge": np.array([con["sense"] == ">=" for con in c.constraints.values()]),
     }
     np.savez_compressed(OUT / "cqm_noisy_circles.npz", **cq)
     # clustering_cqm_2 with subindex attrs from disconnected_components is only valid on a connected graph: noisy_moons
