@@ -404,8 +404,8 @@ def main():
                          "wave), OpenMP over reads",
                "parity_check": {"reads": int(len(sel)), "read_indices": [int(sel[0]), int(sel[len(sel) // 2]), int(sel[-1])],
                                 "final_states_identical_to_gpu": bool(np.array_equal(cpu_states, gpu_states)),
-                                "energies_bitwise_identical_to_gpu": bool(np.array_equal((cpu_energies - model.offset).view(np.uint64),
-                                                                                         gpu_e.view(np.uint64)))}}
+                                "energies_bitwise_identical_to_gpu": bool(np.array_equal(cpu_energies.view(np.uint64),
+                                                                                         (gpu_e + model.offset).view(np.uint64)))}}
     best_weak = float(energies_dev.min().item() + model.offset)
 
     # ---- the config AS STATED: job_reads x job_sweeps, reads split over the ranks (strong scaling), once ---------------
@@ -447,12 +447,16 @@ def main():
         _, viol = ctx.decode_onehot(jstates, cells, args.clusters, on_value=1, min_size=model.meta["min_size"], want_labels=False)
         feasible = allsum(float(((viol[:, 0] == 0) & (viol[:, 1] == 0)).sum()))
         onehot_ok = allsum(float((viol[:, 0] == 0).sum()))
+        bad_cells = allsum(float(viol[:, 0].sum()))
+        small_clusters = allsum(float(viol[:, 1].sum()))
         ej = jenergies.cpu().numpy() + model.offset
         best_job = -allmax(-float(ej.min()))
         job = {"reads": args.job_reads, "num_sweeps": job_sweeps, "num_sweeps_stated": args.job_sweeps, "reads_per_rank": int(Rj),
                "seconds": t_job, "value": job_attempts / t_job, "unit": UNIT, "scaling": "strong",
                "read_waves_per_gpu": float(Rj / 32 / (148 * 16)),
                "feasible_fraction": feasible / args.job_reads, "onehot_satisfied_fraction": onehot_ok / args.job_reads,
+               "mean_cells_not_onehot_per_read": bad_cells / args.job_reads, "cells": cells,
+               "mean_clusters_below_min_size_per_read": small_clusters / args.job_reads,
                "best_energy": best_job, "kernel_ms": allmax(jst.ms_anneal), "vs_weak_value_per_gpu": (job_attempts / t_job / world) / rate}
         if ncj:
             # the CPU arm on the first reads of the job: the converged target of the time-to-best-energy figure, and one more
@@ -461,8 +465,7 @@ def main():
             target = float(cej.min())
             job["cpu_arm"] = {"reads": int(ncj), "seconds": dtj, "value": vj, "best_energy": target,
                               "final_states_identical_to_gpu": bool(np.array_equal(csj, jstates[:ncj].cpu().numpy())),
-                              "energies_bitwise_identical_to_gpu": bool(np.array_equal((cej - model.offset).view(np.uint64),
-                                                                                       (ej[:ncj] - model.offset).view(np.uint64)))}
+                              "energies_bitwise_identical_to_gpu": bool(np.array_equal(cej.view(np.uint64), ej[:ncj].view(np.uint64)))}
         else:
             target = None
         if world > 1:   # every rank needs the target to count its hits

@@ -186,6 +186,23 @@ int qa_gather_samples(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *s
 int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int32_t num_reads, const int8_t *states,
                      int32_t on_value, int32_t min_size, int32_t *labels_out, int32_t *violations_out);
 
+/* Duplicate aggregation (dimod SampleSet.aggregate(): identical samples merged, num_occurrences summed) on the device:
+ * rows are hashed (2 x 64 bit), sorted by hash, neighbours compared byte for byte.  first_index_out[u] = the first read of
+ * the u-th distinct sample, in order of first occurrence; count_out[u] = its number of occurrences (both sized num_reads).
+ * Only 8 bytes per read leave the device. */
+int qa_aggregate_reads(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *states, int32_t *num_unique_out,
+                       int32_t *first_index_out, int32_t *count_out);
+
+/* Device-resident state matrices for callers without a device allocator of their own (the Python host layer): with
+ * return_samples='best_k' the [R][n] state matrix is created, annealed, ranked and reduced to k rows on the device.
+ * qa_random_states: +-1 states from a counter-based generator, spin (r, v) = bit (v & 63) of
+ * splitmix64-mix(seed, first_read + r, v >> 6) -- a function of the GLOBAL read index, so any sharding gives the same states
+ * (schedule.counter_spin_states is the same function in numpy).  states_out: host or device. */
+int qa_dev_alloc(qa_ctx *ctx, int64_t bytes, void **out);
+int qa_dev_free(qa_ctx *ctx, void *p);
+int qa_dev_copy(qa_ctx *ctx, void *dst, const void *src, int64_t bytes);   /* any direction, blocking */
+int qa_random_states(qa_ctx *ctx, uint64_t seed, int64_t first_read, int32_t num_reads, int32_t n, int8_t *states_out);
+
 /* Lowest value and its first index (SampleSet.first; the per-rank half of the multi-GPU best-sample gather):
  * warp-shuffle min-reduction, ties to the lower index.  values: host or device pointer. */
 int qa_argmin(qa_ctx *ctx, int64_t count, const double *values, double *best_value, int64_t *best_index);

@@ -101,6 +101,11 @@ SIGNATURES = {
     "qa_build_dqm_onehot": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _i32, C.POINTER(_p), C.POINTER(C.c_double)]),
     "qa_build_cqm_penalty": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _i32, C.c_double, C.c_double, C.POINTER(_p), C.POINTER(C.c_double)]),
     "qa_energy_argmin": (C.c_int, [_p, _p, _i32, _p, _p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(QAStats)]),
+    "qa_aggregate_reads": (C.c_int, [_p, _i32, _i32, _p, C.POINTER(_i32), _p, _p]),
+    "qa_dev_alloc": (C.c_int, [_p, _i64, C.POINTER(_p)]),
+    "qa_dev_free": (C.c_int, [_p, _p]),
+    "qa_dev_copy": (C.c_int, [_p, _p, _p, _i64]),
+    "qa_random_states": (C.c_int, [_p, C.c_uint64, _i64, _i32, _i32, _p]),
     "qa_argmin": (C.c_int, [_p, _i64, _p, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "qa_debug_pack_slabs": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "qa_sort_reads": (C.c_int, [_p, _i32, _p, _p]),

@@ -39,6 +39,16 @@ def _sampler(sampler):
     return _default_sampler
 
 
+def _on_device(sampler, device_build) -> bool:
+    """Models are built by the qa_build_* kernels when the sampler can (ours); ``device_build=False`` forces the host builders."""
+    return hasattr(sampler, "build_on_device") if device_build is None else bool(device_build)
+
+
+def _close(model):
+    if hasattr(model, "gm"):      # a DeviceModel owns a device handle
+        model.close()
+
+
 def _sample(sampler, model, quiet_kwargs: dict, sa_kwargs: dict):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", UserWarning)  # label / chain_strength / return_embedding are QPU-only
@@ -116,12 +126,19 @@ def _write_labels(G, S0, S1, label, how, color=0):
 
 
 def clustering_bqm(G, iteration, dirs, solver, gamma_factor, color=0, terminate_on="once", size_limit=40, iter_limit=2,
-                   chain_strength=None, sampler=None, structured=True, **sa_kwargs):
+                   chain_strength=None, sampler=None, structured=True, device_build=None, **sa_kwargs):
     """2-way cut+balance partition (BQM_clustering.py:25-203); returns the SampleSet of this level."""
-    model = models.cut_balance_model(G, gamma_factor, k=8, structured=structured)
+    smp = _sampler(sampler)
+    if structured and _on_device(smp, device_build):
+        model = smp.build_on_device("cut_balance", G, gamma_factor=gamma_factor, k=8.0)
+    else:
+        model = models.cut_balance_model(G, gamma_factor, k=8, structured=structured)
     sa_kwargs.setdefault("num_reads", 500)  # BQM_clustering.py:52
-    response = _sample(_sampler(sampler), model, {"label": str(dirs.get("name", "")) + "_" + str(solver),
-                                                   "chain_strength": chain_strength}, sa_kwargs)
+    try:
+        response = _sample(smp, model, {"label": str(dirs.get("name", "")) + "_" + str(solver),
+                                        "chain_strength": chain_strength}, sa_kwargs)
+    finally:
+        _close(model)
     S0, S1 = _split(G, response)
     go, how = bqm_rule(terminate_on, len(S0), len(S1), response.record.energy, iteration, size_limit, iter_limit)
     label = "label" + str(iteration)
@@ -130,7 +147,7 @@ def clustering_bqm(G, iteration, dirs, solver, gamma_factor, color=0, terminate_
         for part in (S0, S1):
             clustering_bqm(G.subgraph(part), iteration + 1, dirs, solver, gamma_factor, color=color + 20, terminate_on=terminate_on,
                            size_limit=size_limit, iter_limit=iter_limit, chain_strength=chain_strength, sampler=sampler,
-                           structured=structured, **sa_kwargs)
+                           structured=structured, device_build=device_build, **sa_kwargs)
     if how is not None and not (go and how == "split"):
         _write_labels(G, S0, S1, label, how)
     return response
@@ -169,37 +186,58 @@ def clustering_bqm_3(G, iteration, dirs, solver, gamma_factor, color=0, terminat
 
 
 def clustering_dqm(G, num_of_clusters, gamma, sampler=None, penalty=None, semantics="as_written", structured=True,
-                   **sa_kwargs):
+                   device_build=None, **sa_kwargs):
     """k-way DQM clustering (DQM_clustering.py:24-47): returns a SampleSet of case indices per cell."""
-    model = models.dqm_model(G, num_of_clusters, gamma, penalty=penalty, semantics=semantics, structured=structured)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", UserWarning)
-        sampleset = _sampler(sampler).sample_dqm(model, label="DQM - scRAN-seq", **sa_kwargs)
-    return sampleset
+    smp = _sampler(sampler)
+    if structured and _on_device(smp, device_build):
+        model = smp.build_on_device("dqm", G, num_of_clusters=num_of_clusters, gamma=gamma, penalty=penalty, semantics=semantics)
+    else:
+        model = models.dqm_model(G, num_of_clusters, gamma, penalty=penalty, semantics=semantics, structured=structured)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            return smp.sample_dqm(model, label="DQM - scRAN-seq", **sa_kwargs)
+    finally:
+        _close(model)
 
 
-def clustering_cqm(G, num_of_clusters, sampler=None, onehot_penalty=None, size_penalty=None, min_size=20, **sa_kwargs):
+def _cqm(G, num_of_clusters, sampler, onehot_penalty, size_penalty, min_size, subindex, device_build, sa_kwargs):
+    smp = _sampler(sampler)
+    if _on_device(smp, device_build):
+        model = smp.build_on_device("cqm", G, num_of_clusters=num_of_clusters, min_size=min_size, onehot_penalty=onehot_penalty,
+                                    size_penalty=size_penalty, subindex=subindex)
+    else:
+        model = models.cqm_model(G, num_of_clusters, min_size, onehot_penalty, size_penalty, subindex=subindex)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            return smp.sample_cqm(model, label="CQM - scRAN-seq", **sa_kwargs)
+    finally:
+        _close(model)
+
+
+def clustering_cqm(G, num_of_clusters, sampler=None, onehot_penalty=None, size_penalty=None, min_size=20, device_build=None,
+                   **sa_kwargs):
     """k-way CQM clustering with one-hot and minimum-size constraints (CQM_clustering.py:25-55)."""
-    model = models.cqm_model(G, num_of_clusters, min_size, onehot_penalty, size_penalty)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", UserWarning)
-        return _sampler(sampler).sample_cqm(model, label="CQM - scRAN-seq", **sa_kwargs)
+    return _cqm(G, num_of_clusters, sampler, onehot_penalty, size_penalty, min_size, None, device_build, sa_kwargs)
 
 
-def clustering_cqm_2(G, num_of_clusters, sampler=None, onehot_penalty=None, size_penalty=None, min_size=20, **sa_kwargs):
+def clustering_cqm_2(G, num_of_clusters, sampler=None, onehot_penalty=None, size_penalty=None, min_size=20, device_build=None,
+                     **sa_kwargs):
     """As ``clustering_cqm`` but variables are named by the node attribute ``subindex`` (CQM_clustering.py:57-91)."""
     sub = [G.nodes[i]["subindex"] for i in G.nodes]
-    model = models.cqm_model(G, num_of_clusters, min_size, onehot_penalty, size_penalty, subindex=sub)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", UserWarning)
-        return _sampler(sampler).sample_cqm(model, label="CQM - scRAN-seq", **sa_kwargs)
+    return _cqm(G, num_of_clusters, sampler, onehot_penalty, size_penalty, min_size, sub, device_build, sa_kwargs)
 
 
-def graph_subsampling(G, gamma, solver="hybrid", sampler=None, **sa_kwargs):
+def graph_subsampling(G, gamma, solver="hybrid", sampler=None, device_build=None, **sa_kwargs):
     """Pruning QUBO (QA_subsampling.py:24-97): labels nodes ``label1`` in {0, 1} and returns the SampleSet."""
-    model = models.subsampling_model(G, gamma)
+    smp = _sampler(sampler)
+    model = smp.build_on_device("subsampling", G, gamma=gamma) if _on_device(smp, device_build) else models.subsampling_model(G, gamma)
     sa_kwargs.setdefault("num_reads", 100)  # QA_subsampling.py:37
-    response = _sample(_sampler(sampler), model, {"label": "prun_data", "chain_strength": 4}, sa_kwargs)
+    try:
+        response = _sample(smp, model, {"label": "prun_data", "chain_strength": 4}, sa_kwargs)
+    finally:
+        _close(model)
     S0, S1 = _split(G, response)
     _label(G, S0, "label1", 0)
     _label(G, S1, "label1", 1)

@@ -15,10 +15,11 @@ namespace {
 __global__ void k_energy_keys(int32_t count, const double *e, unsigned long long *keys, int32_t *idx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    idx[i] = i;
+    if (!e) return;   // index ramp only
     unsigned long long b = (unsigned long long)__double_as_longlong(e[i] + 0.0);   // -0.0 and +0.0 tie
     b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
     keys[i] = b;
-    idx[i] = i;
 }
 
 // samples_out[r] = states[order[r]] for r < k  (one block per output row, coalesced 16-byte copies when aligned)
@@ -53,6 +54,69 @@ __global__ void k_count_small_clusters(int32_t reads, int32_t K, int32_t min_siz
     int bad = 0;
     for (int k = 0; k < K; ++k) bad += sizes[(int64_t)r * K + k] < min_size;
     violations[2 * r + 1] = bad;
+}
+
+// counter-based initial states: spin (r, v) = bit (v & 63) of splitmix64(seed, global read r, word v >> 6); 1 -> -1.
+// Depends only on (seed, global read index, variable): identical for any sharding of the reads over GPUs, and restated in
+// numpy by schedule.counter_spin_states for the host path.
+__host__ __device__ inline unsigned long long qa_mix64(unsigned long long seed, unsigned long long r, unsigned long long w) {
+    unsigned long long z = (seed + 1ull) * 0xD1342543DE82EF95ull + r * 0x9E3779B97F4A7C15ull + w * 0xC2B2AE3D27D4EB4Full;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_random_states(unsigned long long seed, int64_t first_read, int32_t reads, int32_t n, int8_t *states) {
+    const int64_t words = ((int64_t)n + 63) / 64;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)reads * words) return;
+    const int64_t r = t / words, w = t % words;
+    const unsigned long long bits = qa_mix64(seed, (unsigned long long)(first_read + r), (unsigned long long)w);
+    int8_t *row = states + r * (int64_t)n + w * 64;
+    const int lim = (int)min((int64_t)64, (int64_t)n - w * 64);
+    for (int i = 0; i < lim; ++i) row[i] = ((bits >> i) & 1ull) ? -1 : 1;
+}
+
+// 2 x 64-bit hash of every row (one block per read): duplicate detection for SampleSet.aggregate()
+__global__ void k_hash_rows(int32_t n, const int8_t *states, unsigned long long *h1, unsigned long long *h2) {
+    const int8_t *row = states + (int64_t)blockIdx.x * n;
+    unsigned long long a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long x = (unsigned long long)(unsigned char)row[i] + 1ull;
+        a += qa_mix64(x, (unsigned long long)i, 1ull);          // order-independent sum of position-keyed mixes
+        b ^= qa_mix64(x, (unsigned long long)i, 2ull) * 0x9E3779B97F4A7C15ull;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b ^= __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __shared__ unsigned long long sa[32], sb[32];
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a += sa[w]; b ^= sb[w]; }
+        h1[blockIdx.x] = a;
+        h2[blockIdx.x] = b;
+    }
+}
+
+// sorted position p (reads ordered by h1, ties in read order): head[p] = 1 when read idx[p] differs from read idx[p-1]
+// (both hashes, then the full rows: one block per position)
+__global__ void k_mark_heads(int32_t n, const int8_t *states, const unsigned long long *h1s, const int32_t *idx,
+                             const unsigned long long *h2, int32_t *head) {
+    const int p = blockIdx.x;
+    if (p == 0) { if (threadIdx.x == 0) head[0] = 1; return; }
+    const int a = idx[p], b = idx[p - 1];
+    __shared__ int differ;
+    if (threadIdx.x == 0) differ = (h1s[p] != h1s[p - 1] || h2[a] != h2[b]) ? 1 : 0;
+    __syncthreads();
+    if (!differ) {
+        const int8_t *ra = states + (int64_t)a * n, *rb = states + (int64_t)b * n;
+        int d = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d |= ra[i] != rb[i];
+        if (d) atomicOr(&differ, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) head[p] = differ;
 }
 
 // stage `bytes` of a caller buffer (host or device) on the device; returns the device pointer to use
@@ -160,6 +224,107 @@ int qa_decode_onehot(qa_ctx *ctx, int32_t cells, int32_t K, int64_t stride, int3
     return QA_OK;
 }
 
+int qa_dev_alloc(qa_ctx *ctx, int64_t bytes, void **out) {
+    if (!ctx || !out || bytes < 0) return fail(QA_ERR_ARG, "bad arguments");
+    *out = nullptr;
+    QA_CUDA(cudaSetDevice(ctx->device));
+    QA_CUDA(cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return QA_OK;
+}
+
+int qa_dev_free(qa_ctx *ctx, void *p) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (!p) return QA_OK;
+    QA_CUDA(cudaSetDevice(ctx->device));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    QA_CUDA(cudaFree(p));
+    return QA_OK;
+}
+
+int qa_dev_copy(qa_ctx *ctx, void *dst, const void *src, int64_t bytes) {
+    if (!ctx || bytes < 0) return fail(QA_ERR_ARG, "bad arguments");
+    if (bytes == 0) return QA_OK;
+    if (!dst || !src) return fail(QA_ERR_ARG, "null pointer");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    QA_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_random_states(qa_ctx *ctx, uint64_t seed, int64_t first_read, int32_t num_reads, int32_t n, int8_t *states_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (num_reads < 0 || n < 0 || first_read < 0) return fail(QA_ERR_ARG, "negative size");
+    if (num_reads == 0 || n == 0) return QA_OK;
+    if (!states_out) return fail(QA_ERR_ARG, "null states_out");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const int64_t bytes = (int64_t)num_reads * n;
+    int8_t *d_out = states_out;
+    const bool out_host = !is_device_ptr(states_out);
+    if (out_host) {
+        int rc = ensure(ctx->states, (size_t)bytes);
+        if (rc) return rc;
+        d_out = (int8_t *)ctx->states.p;
+    }
+    const int64_t threads = (int64_t)num_reads * (((int64_t)n + 63) / 64);
+    k_random_states<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>((unsigned long long)seed, first_read, num_reads, n, d_out);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (out_host) QA_CUDA(cudaMemcpyAsync(states_out, d_out, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QA_OK;
+}
+
+int qa_aggregate_reads(qa_ctx *ctx, int32_t n, int32_t num_reads, const int8_t *states, int32_t *num_unique_out,
+                       int32_t *first_index_out, int32_t *count_out) {
+    if (!ctx) return fail(QA_ERR_ARG, "null context");
+    if (n < 0 || num_reads < 0) return fail(QA_ERR_ARG, "negative size");
+    if (!num_unique_out) return fail(QA_ERR_ARG, "null num_unique_out");
+    *num_unique_out = 0;
+    if (num_reads == 0) return QA_OK;
+    if (!states || !first_index_out || !count_out) return fail(QA_ERR_ARG, "null states / outputs");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const void *d_states = nullptr;
+    int rc = stage_in(ctx, ctx->states, states, (size_t)num_reads * std::max(n, 1), &d_states);
+    if (rc) return rc;
+    const size_t R = (size_t)num_reads;
+    // scratch: h1, h1s, h2 (u64), idx, idxs, head (i32)
+    rc = ensure(ctx->misc, 3 * R * sizeof(unsigned long long) + 3 * R * sizeof(int32_t) + 64);
+    if (rc) return rc;
+    unsigned long long *h1 = (unsigned long long *)ctx->misc.p, *h1s = h1 + R, *h2 = h1s + R;
+    int32_t *idx = (int32_t *)(h2 + R), *idxs = idx + R, *head = idxs + R;
+    k_hash_rows<<<num_reads, 128, 0, ctx->stream>>>(n, (const int8_t *)d_states, h1, h2);
+    k_energy_keys<<<(num_reads + 255) / 256, 256, 0, ctx->stream>>>(num_reads, nullptr, nullptr, idx);   // idx = 0 .. R-1
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, h1, h1s, idx, idxs, num_reads, 0, 64, ctx->stream);
+    rc = ensure(ctx->cubtmp, tmp);
+    if (rc) return rc;
+    cudaError_t ce = cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, tmp, h1, h1s, idx, idxs, num_reads, 0, 64, ctx->stream);
+    if (ce != cudaSuccess) return fail(QA_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(ce));
+    k_mark_heads<<<num_reads, 128, 0, ctx->stream>>>(n, (const int8_t *)d_states, h1s, idxs, h2, head);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches += 11;
+    // the group structure is tiny next to the state matrix: finish on the host (R x 8 bytes leave the device)
+    std::vector<int32_t> hidx(R), hhead(R);
+    QA_CUDA(cudaMemcpyAsync(hidx.data(), idxs, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaMemcpyAsync(hhead.data(), head, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
+    // groups are runs of the hash-sorted order (stable: inside a run reads ascend); two DIFFERENT samples with equal 128-bit
+    // hashes would split a run of a third one -- merge runs of the same representative by comparing against all run heads
+    // of the same h1 (the full-row compare above already separated them, so this only matters for interleaved collisions)
+    std::vector<std::pair<int32_t, int32_t>> groups;   // (first read index, count)
+    for (size_t p = 0; p < R; ++p) {
+        if (hhead[p]) groups.emplace_back(hidx[p], 1);
+        else groups.back().second++;
+    }
+    std::sort(groups.begin(), groups.end());          // dimod.SampleSet.aggregate keeps the order of first occurrence
+    for (size_t u = 0; u < groups.size(); ++u) {
+        first_index_out[u] = groups[u].first;
+        count_out[u] = groups[u].second;
+    }
+    *num_unique_out = (int32_t)groups.size();
+    return QA_OK;
+}
+
 int qa_argmin(qa_ctx *ctx, int64_t count, const double *values, double *best_value, int64_t *best_index) {
     if (!ctx) return fail(QA_ERR_ARG, "null context");
     if (count < 0) return fail(QA_ERR_ARG, "negative count");
@@ -206,7 +371,8 @@ int qa_debug_pack_slabs(int32_t n, const int32_t *rowptr, const int32_t *col, co
     }
     const int64_t var_off[2] = {0, n};
     RpPacked pk;
-    if (!pack_replay_slabs(1, var_off, rp.data(), col, val, ngroups, hg, hc, pk)) return 0;
+    if (!pack_replay_slabs(1, var_off, rp.data(), col, val, ngroups, hg, hc, 32, pk) &&
+        !pack_replay_slabs(1, var_off, rp.data(), col, val, ngroups, hg, hc, 64, pk)) return 0;
     *nslabs_out = pk.nslabs[0];
     *bytes_out = (int64_t)pk.slabs.size();
     *uniform_out = pk.uniform ? 1 : 0;

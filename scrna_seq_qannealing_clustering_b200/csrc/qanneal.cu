@@ -1273,6 +1273,7 @@ struct qa_model {
     uint32_t *rp_off = nullptr;
     bool rp_built = false, rp_ok = false;
     bool rp_uniform = false;   // every block holds exactly RP_D variables
+    int rp_slots = 32;         // half-word slots per warp the slabs were packed for (32 or 64)
     bool rp_adj_sorted = false; // adjacency lists ascending: field set-up through the slab ring
     bool groups_i32 = false;   // every group term a*(a - s*(M+kappa)) fits 32-bit integers
 };
@@ -1525,7 +1526,8 @@ struct RpPacked {
 };
 
 bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, const int32_t *col, const double *val, int ngroups,
-                       const std::vector<int32_t> &hg, const std::vector<int32_t> &hc, RpPacked &out) {
+                       const std::vector<int32_t> &hg, const std::vector<int32_t> &hc, int slots, RpPacked &out) {
+    const int RP_MAXBW = slots - 1;   // foreign half-words per block
     std::vector<uint32_t> &off = out.off;
     std::vector<unsigned char> &slabs = out.slabs;
     out.blk_base.assign(P, 0);
@@ -1618,7 +1620,7 @@ bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, con
                 RpEntry en;
                 en.J = nb.J;
                 en.zero = 0u;
-                en.B = (uint32_t)(30 - 2 * (nb.j & 15)) | ((uint32_t)(wj == own ? 0 : slot_of[wj]) << 7) | ((uint32_t)nb.j << 12);
+                en.B = (uint32_t)(30 - 2 * (nb.j & 15)) | ((uint32_t)(wj == own ? 0 : slot_of[wj]) << 7) | ((uint32_t)nb.j << RP_J_SHIFT);
                 E.push_back(en);
             };
             for (int i = 0; i < nv; ++i) {
@@ -1628,7 +1630,7 @@ bool pack_replay_slabs(int P, const int64_t *var_off, const int32_t *rowptr, con
                     RpEntry en;
                     en.J = 0.0;          // fma(0, sigma, f) == f
                     en.zero = 0u;
-                    en.B = 30u | ((uint32_t)(v0 + i) << 12);   // slot 0
+                    en.B = 30u | ((uint32_t)(v0 + i) << RP_J_SHIFT);   // slot 0
                     E.push_back(en);
                 }
             }
@@ -1696,8 +1698,13 @@ int build_replay_tables(qa_model *M) {
         QA_CUDA(cudaMemcpy(hc.data(), M->coef, npad * sizeof(int32_t), cudaMemcpyDeviceToHost));
     }
     RpPacked pk;
-    if (!pack_replay_slabs(M->num_problems, M->var_off.data(), rowptr.data(), col.data(), val.data(), M->ngroups, hg, hc, pk))
-        return QA_OK;   // the model does not fit the slab format: rp_ok stays false
+    // 32 half-word slots per warp when the blocks fit (4 KB per warp), else 64 (scattered neighbourhoods)
+    M->rp_slots = 32;
+    if (!pack_replay_slabs(M->num_problems, M->var_off.data(), rowptr.data(), col.data(), val.data(), M->ngroups, hg, hc, 32, pk)) {
+        M->rp_slots = 64;
+        if (!pack_replay_slabs(M->num_problems, M->var_off.data(), rowptr.data(), col.data(), val.data(), M->ngroups, hg, hc, 64, pk))
+            return QA_OK;   // the model does not fit the slab format: rp_ok stays false
+    }
     const std::vector<uint32_t> &off = pk.off;
     const std::vector<unsigned char> &slabs = pk.slabs;
     const std::vector<int64_t> &blk_base = pk.blk_base;
@@ -1864,15 +1871,20 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         if (nw < 1 || nw > RP_MAX_WARPS) {
             nw = 1;
             while (nw < RP_MAX_WARPS && nw < tpp) nw *= 2;
-            while (nw > 1 && rp_smem_bytes(nw, mg, ctx->rp_smem_base) > (size_t)(226 * 1024 / RP_MIN_CTAS - 1024)) nw /= 2;   // RP_MIN_CTAS CTAs per SM
+            while (nw > 1 && rp_smem_bytes(nw, mg, ctx->rp_smem_base, M->rp_slots) > (size_t)(226 * 1024 / RP_MIN_CTAS - 1024)) nw /= 2;   // RP_MIN_CTAS CTAs per SM
             // few tiles: prefer narrower CTAs on every SM to full CTAs on some of them
             while (nw > 1 && (int64_t)P * ((tpp + nw - 1) / nw) < 2 * (int64_t)ctx->num_sms) nw /= 2;
         }
         const int64_t gpp = (tpp + nw - 1) / nw;
         const int64_t total_items = (int64_t)P * gpp;
-        size_t smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
-        const void *fn = !groups ? (const void *)k_anneal_replay<0>
-                                 : (M->groups_i32 ? (const void *)k_anneal_replay<1> : (const void *)k_anneal_replay<2>);
+        size_t smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base, M->rp_slots);
+        const void *fn = nullptr;
+        if (M->rp_slots == 32)
+            fn = !groups ? (const void *)k_anneal_replay<0, 32>
+                         : (M->groups_i32 ? (const void *)k_anneal_replay<1, 32> : (const void *)k_anneal_replay<2, 32>);
+        else
+            fn = !groups ? (const void *)k_anneal_replay<0, 64>
+                         : (M->groups_i32 ? (const void *)k_anneal_replay<1, 64> : (const void *)k_anneal_replay<2, 64>);
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
         QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, nw * 32, smem, cudaOccupancyDefault));
@@ -1921,7 +1933,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
                 QA_CUDA(cudaStreamSynchronize(ctx->stream));
                 if (fl[0] == QA_ERR_SMEM_BASE) {
                     ctx->rp_smem_base = (unsigned)fl[1];
-                    smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base);
+                    smem = rp_smem_bytes(nw, mg, ctx->rp_smem_base, M->rp_slots);
                     QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
                     QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));

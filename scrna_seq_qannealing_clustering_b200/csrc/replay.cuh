@@ -43,8 +43,9 @@
 #pragma once
 
 constexpr int RP_D = 16;                      // variables per block, at most (= one half-word of spins)
-constexpr int RP_SLOTS = 32;                  // half-word slots per warp: slot 0 = the block's own half-word
-constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign half-words per block
+constexpr int RP_SLOTS = 64;                  // half-word slots per warp, at most: slot 0 = the block's own half-word.  Two kernel
+                                              // instances: 32 slots (4 KB per warp; local graphs such as config 3) and 64 slots
+                                              // (8 KB; scattered neighbourhoods such as the 1000-cell sub-problems of config 4)
 #ifndef RP_CAP
 #define RP_CAP 448     // entry slots per slab (pre parts in rounds of 4, then the seq parts)
 #endif
@@ -61,9 +62,9 @@ constexpr int RP_MAXBW = RP_SLOTS - 1;        // foreign half-words per block
 #define RP_DIST 2     // slabs are requested this many blocks ahead of the first warp that will need them (< RP_STAGES)
 #endif
 static_assert(RP_DIST < RP_STAGES, "the ring must hold the block in use and the requested ones");
-constexpr int RP_SF_BYTES = RP_SLOTS * 32 * 4;   // per warp: {S | F << 16}[slot][lane]; 4 KB, aligned to its size
 constexpr int RP_PS_BYTES = RP_D * 32 * 8;       // per warp: partial sums [row][lane] (push phase: the block's fields)
-constexpr uint32_t RP_SLOT_MASK = (uint32_t)(RP_SLOTS - 1) << 7;
+__host__ __device__ constexpr int rp_sf_bytes(int slots) { return slots * 32 * 4; }   // per warp: [slot][lane] words, aligned to its size
+__host__ __device__ constexpr uint32_t rp_slot_mask(int slots) { return (uint32_t)(slots - 1) << 7; }
 #ifndef RP_MAX_WARPS
 #define RP_MAX_WARPS 8    // warps per CTA (upper bound; the host picks a power of two)
 #endif
@@ -95,9 +96,10 @@ struct __align__(16) RpEntry {
     double J;      // the coupling (0.0 for padding entries: fma(0, sigma, f) == f)
     uint32_t zero; // low word of sigma: the entry's LDS.128 delivers the register pair {0, B} the DFMA multiplies by
     uint32_t B;    // bits 0-4: 30 - 2 * (j & 15) (left shift that brings the neighbour's D bit to bit 31, its F bit to bit 30);
-                   // bits 7-11: slot; bits 12-31: neighbour j (local variable index, < 2^20)
+                   // bits 7-12: slot; bits 13-31: neighbour j (local variable index, < 2^19)
 };
-constexpr int RP_MAX_VARS = 1 << 20;
+constexpr int RP_MAX_VARS = 1 << 19;
+constexpr int RP_J_SHIFT = 13;
 constexpr int RP_STAGE_BYTES = (int)sizeof(RpHdr) + (RP_CAP + 8) * (int)sizeof(RpEntry);   // + two rounds of read-ahead slack
 static_assert(RP_STAGE_BYTES % 16 == 0, "stage alignment");
 
@@ -242,7 +244,7 @@ __device__ __forceinline__ void rp_stage_wait() {
 // MODE 2: push sweep (neal's eager form).  MODE 3: field set-up f[v] = h_v + sum_j J_vj s_j in neal's get_flip_energy order,
 // for models whose adjacency lists are ascending (then adjacency order = pre entries u < v0, seq entries, later entries).
 // GROUPS: 0 none, 1 rank-1 groups with 32-bit exact integer arithmetic (host-checked ranges), 2 with 64-bit.
-template <int MODE, int GROUPS>
+template <int MODE, int GROUPS, int SLOTS>
 __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
     const int lane = threadIdx.x & 31;
     const double thr = 44.36142 / beta;
@@ -326,20 +328,20 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) qb[k] = lds_v4(a + 64u + 16u * k);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qa[k].w & RP_SLOT_MASK) | sfb);
+                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qa[k].w & rp_slot_mask(SLOTS)) | sfb);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) rp_add_entry(p, qa[k], w[k]);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) qa[k] = lds_v4(a + 128u + 16u * k);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qb[k].w & RP_SLOT_MASK) | sfb);
+                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qb[k].w & rp_slot_mask(SLOTS)) | sfb);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) rp_add_entry(p, qb[k], w[k]);
                             a += 128u;
                         }
                         if (r < nr) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qa[k].w & RP_SLOT_MASK) | sfb);
+                            for (int k = 0; k < 4; ++k) w[k] = lds_vu32(((uint32_t)qa[k].w & rp_slot_mask(SLOTS)) | sfb);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) rp_add_entry(p, qa[k], w[k]);
                             a += 64u;
@@ -427,7 +429,7 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                         const uint32_t nl = lds_u32(hdr + RP_H_ROWB + 4u * (uint32_t)i) & 0xffffu;
                         for (uint32_t k = 0; k < nl; ++k) {
                             const int4 q = lds_v4(a + 16u * k);
-                            rp_add_entry(p, q, lds_vu32(((uint32_t)q.w & RP_SLOT_MASK) | sfb));
+                            rp_add_entry(p, q, lds_vu32(((uint32_t)q.w & rp_slot_mask(SLOTS)) | sfb));
                         }
                         a += nr * 64u;
                         if (p != f0) __stcg(fB + i * 32, p);
@@ -454,7 +456,7 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
                     double fv = __ldg(c.h + v0 + i);
                     auto add1 = [&](uint32_t ad) {
                         const int4 q = lds_v4(ad);
-                        const uint32_t w = lds_vu32(((uint32_t)q.w & RP_SLOT_MASK) | sfb);
+                        const uint32_t w = lds_vu32(((uint32_t)q.w & rp_slot_mask(SLOTS)) | sfb);
                         const uint32_t x = w << ((uint32_t)q.w & 31u);
                         fv = fv + __hiloint2double(q.y ^ (int)(x & 0x80000000u), q.x);   // down: -J
                     };
@@ -523,7 +525,7 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 #pragma unroll 4
                     for (uint32_t k = 0; k < cnt; ++k) {
                         const int4 q = lds_v4(ab + 16u * k);
-                        const int j = (int)((uint32_t)q.w >> 12);
+                        const int j = (int)((uint32_t)q.w >> RP_J_SHIFT);
                         const double d = __hiloint2double(q.y ^ sgn, q.x) * 2.0;   // exact
                         if ((uint32_t)(j - v0) < (uint32_t)nv) {   // uniform: neighbour staged in this block
                             const uint32_t cad = psb + ((uint32_t)(j - v0) << 8);
@@ -562,8 +564,9 @@ __device__ void rp_pass(RpCtx &c, double beta, bool has_next_pass) {
 
 // The set-up pass as a real call with the context passed BY VALUE: its registers do not add to the pressure of the sweep
 // loops.
+template <int SLOTS>
 __device__ __noinline__ uint32_t rp_setup_pass(RpCtx c) {
-    rp_pass<3, 0>(c, 1.0, true);
+    rp_pass<3, 0, SLOTS>(c, 1.0, true);
     return c.gb;
 }
 
@@ -589,7 +592,7 @@ __device__ __forceinline__ double rp_field_direct(const ProblemDesc &D, const ui
     return fv;
 }
 
-// Shared-memory layout: [slab stages][mbarriers][CTA scratch][lambda][kappa][group counters] then, aligned to RP_SF_BYTES in
+// Shared-memory layout: [slab stages][mbarriers][CTA scratch][lambda][kappa][group counters] then, aligned to rp_sf_bytes(SLOTS) in
 // the shared window (so that a slot address is formed by OR), one slot region per warp, then one partial-sum region per warp.
 // `smem_base` is the shared-window offset of the dynamic allocation (1 KB on sm_100: the system-reserved bytes); the kernel
 // verifies the assumption.
@@ -599,15 +602,17 @@ __host__ __device__ inline size_t rp_fixed_bytes(int nw, int max_groups) {
     b += sizeof(int) * (size_t)max_groups * nw * 32;
     return b;
 }
-__host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned smem_base) {
+__host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned smem_base, int slots) {
     const size_t fixed = rp_fixed_bytes(nw, max_groups);
-    const size_t pad = (RP_SF_BYTES - (smem_base + fixed) % RP_SF_BYTES) % RP_SF_BYTES;
-    return fixed + pad + (size_t)nw * (RP_SF_BYTES + RP_PS_BYTES);
+    const size_t sf = (size_t)rp_sf_bytes(slots);
+    const size_t pad = (sf - (smem_base + fixed) % sf) % sf;
+    return fixed + pad + (size_t)nw * (sf + RP_PS_BYTES);
 }
 constexpr int QA_ERR_SMEM_BASE = -100;   // internal: the dynamic shared memory does not start where the host assumed
 
-template <int GROUPS>
+template <int GROUPS, int SLOTS>
 __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_replay(AnnealParams P) {
+    constexpr uint32_t RP_SF_BYTES = (uint32_t)rp_sf_bytes(SLOTS);
     extern __shared__ __align__(16) unsigned char rp_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -756,7 +761,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
         // ---- local fields in neal's get_flip_energy order: through the slab ring when the adjacency lists are ascending,
         // else row by row from the CSR
         if (P.rp_slab_init) {
-            if (total_sweeps > 0) c.gb = rp_setup_pass(c);
+            if (total_sweeps > 0) c.gb = rp_setup_pass<SLOTS>(c);
         } else {
             int e0 = __ldg(D.rowptr);
             for (int v = 0; v < n; ++v) {
@@ -778,10 +783,10 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                     printf("[qa sweep] %lld beta %.4g mode %s clock %lld\n", done, beta, push ? "push" : "replay", clock64());
 #endif
                 if (push) {
-                    rp_pass<2, GROUPS>(c, beta, more);
+                    rp_pass<2, GROUPS, SLOTS>(c, beta, more);
                 } else {
                     const unsigned acc0 = c.st.acc;
-                    rp_pass<0, GROUPS>(c, beta, more);
+                    rp_pass<0, GROUPS, SLOTS>(c, beta, more);
                     if (more) {  // CTA-uniform hand-over decision
                         unsigned wacc = c.st.acc - acc0;
 #pragma unroll
@@ -792,7 +797,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
                         if (threadIdx.x == 0) acc_sh[acc_par ^ 1] = 0u;
                         acc_par ^= 1;
                         if (tot * 1000ull < (unsigned long long)P.switch_permille * (unsigned long long)n * (unsigned long long)cta_reads) {
-                            rp_pass<1, 0>(c, beta, true);
+                            rp_pass<1, 0, SLOTS>(c, beta, true);
                             push = true;
                         }
                     }

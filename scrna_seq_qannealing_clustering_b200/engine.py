@@ -27,6 +27,46 @@ def _as(x, dtype, name):
     return a
 
 
+class DeviceBuffer:
+    """A device allocation of the library (``qa_dev_alloc``) with a shape: lets the host layer keep a state matrix on the
+    GPU from creation to the top-k export without depending on a tensor library.  Quacks like a tensor for ``_lib.ptr``."""
+
+    def __init__(self, ctx: "Context", shape, dtype=np.int8):
+        self.ctx = ctx
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(_lib.load().qa_dev_alloc(ctx._h, self.nbytes, C.byref(p)))
+        self._p = p
+
+    def data_ptr(self) -> int:
+        return int(self._p.value or 0)
+
+    def upload(self, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        if host.nbytes != self.nbytes:
+            raise ValueError("size mismatch")
+        check(_lib.load().qa_dev_copy(self.ctx._h, self._p, ptr(host), self.nbytes))
+        return self
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        check(_lib.load().qa_dev_copy(self.ctx._h, ptr(out), self._p, self.nbytes))
+        return out
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value and getattr(self.ctx, "_h", None):
+            _lib.load().qa_dev_free(self.ctx._h, self._p)
+        self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU + one CUDA stream + reusable scratch (``qa_ctx``)."""
 
@@ -103,6 +143,26 @@ class Context:
         check(_lib.load().qa_decode_onehot(self._h, int(cells), int(num_cases), stride, num_reads, ptr(states), int(on_value),
                                            int(min_size), ptr(labels), ptr(violations)))
         return labels, violations
+
+    def random_states(self, seed: int, first_read: int, num_reads: int, n: int, out=None):
+        """+-1 states of the counter-based generator (``schedule.counter_spin_states`` on the host), written to ``out`` (a
+        ``DeviceBuffer`` / CUDA tensor / numpy array; default: a new ``DeviceBuffer``) without crossing PCIe."""
+        if out is None:
+            out = DeviceBuffer(self, (num_reads, n), np.int8)
+        check(_lib.load().qa_random_states(self._h, int(seed), int(first_read), int(num_reads), int(n), ptr(out)))
+        return out
+
+    def aggregate_reads(self, states):
+        """``SampleSet.aggregate()`` on the device: (first read index of every distinct sample in order of first occurrence,
+        its number of occurrences)."""
+        num_reads, n = int(states.shape[0]), int(states.shape[1])
+        if not _is_tensor(states):
+            states = np.ascontiguousarray(states, dtype=np.int8)
+        first = np.empty(num_reads, dtype=np.int32)
+        count = np.empty(num_reads, dtype=np.int32)
+        nu = C.c_int32()
+        check(_lib.load().qa_aggregate_reads(self._h, n, num_reads, ptr(states), C.byref(nu), ptr(first), ptr(count)))
+        return first[: nu.value].copy(), count[: nu.value].copy()
 
     def argmin(self, values):
         """(lowest value, its first index) by the warp-shuffle reduction kernel; ``values`` numpy or a CUDA tensor (fp64)."""

@@ -347,6 +347,57 @@ def cqm_model(G, num_of_clusters: int, min_size: int = 20, onehot_penalty: Optio
 
 
 # ------------------------------------------------------------------------------------------------
+# everything about a model EXCEPT its vectors: what the host needs when the vectors are built on the device (qa_build_*)
+# ------------------------------------------------------------------------------------------------
+def device_spec(kind: str, G, **p) -> Dict:
+    """Graph arrays, variable labels, penalties and ``meta`` of the model ``kind`` ('cut_balance', 'subsampling', 'dqm',
+    'cqm') -- O(n + m) numpy, no O(n^2) term, no Python loop over pairs.  The vectors come from ``Context.build_*``; they
+    are bit-identical to the host builders above (tests/test_gpu_builders.py)."""
+    labels, eu, ev, w = graph_arrays(G)
+    n = len(labels)
+    graph = (n, eu.astype(np.int32), ev.astype(np.int32), w)
+    if kind == "cut_balance":
+        return {"graph": graph, "labels": labels, "meta": {"kind": "bqm", "builder": "cut_balance", "k": p.get("k", 8.0)}}
+    if kind == "subsampling":
+        return {"graph": graph, "labels": labels, "meta": {"kind": "bqm", "builder": "subsampling", "gamma": p["gamma"]}}
+    K = int(p["num_of_clusters"])
+    if kind == "dqm":
+        gamma, semantics = p["gamma"], p.get("semantics", "as_written")
+        if semantics not in ("as_written", "intended"):
+            raise ValueError("semantics must be 'as_written' or 'intended'")
+        base_lin = gamma * (1 - n / K)
+        if semantics == "as_written":
+            lin = np.full(n, base_lin)
+            last = np.full(n, -1, dtype=np.int64)           # last edge touching every cell (DQM_clustering.py:42-43)
+            idx = np.arange(len(w), dtype=np.int64)
+            np.maximum.at(last, eu, idx)
+            np.maximum.at(last, ev, idx)
+            lin[last >= 0] = w[last[last >= 0]]
+            edge_q_total = -2 * w
+        else:
+            lin = base_lin + _edge_order_sum(n, eu, ev, w)
+            edge_q_total = 2 * gamma - 2 * w
+        A = default_onehot_penalty(n, K, eu, ev, edge_q_total, lin, gamma) if p.get("penalty") is None else float(p["penalty"])
+        meta = {"kind": "dqm", "builder": "dqm", "num_cases": K, "cells": labels, "penalty": A, "gamma": gamma,
+                "semantics": semantics}
+        return {"graph": graph, "labels": [(v, c) for v in labels for c in range(K)], "meta": meta, "penalty": A}
+    if kind == "cqm":
+        min_size = int(p.get("min_size", 20))
+        deg = _edge_order_sum(n, eu, ev, np.ones(len(w)))
+        wdeg = _edge_order_sum(n, eu, ev, np.abs(2 * w))
+        A = float(deg.max() + wdeg.max() + 1.0) if p.get("onehot_penalty") is None else float(p["onehot_penalty"])
+        B = 1.0 if p.get("size_penalty") is None else float(p["size_penalty"])
+        coeffs = slack_coefficients(n - min_size)
+        names = labels if p.get("subindex") is None else list(p["subindex"])
+        var_labels: List[Hashable] = [f"v_{names[i]},{q}" for i in range(n) for q in range(K)]
+        var_labels += [f"slack_cluster_size{j}_{b}" for j in range(K) for b in range(len(coeffs))]
+        meta = {"kind": "cqm", "builder": "cqm", "num_cases": K, "cells": labels, "names": list(names), "min_size": min_size,
+                "onehot_penalty": A, "size_penalty": B, "slack_coefficients": coeffs, "num_cell_variables": n * K}
+        return {"graph": graph, "labels": var_labels, "meta": meta, "onehot_penalty": A, "size_penalty": B, "min_size": min_size}
+    raise ValueError(f"unknown model kind {kind!r}")
+
+
+# ------------------------------------------------------------------------------------------------
 # decoding (plot_and_save.py:36-63 read `.first.sample` this way)
 # ------------------------------------------------------------------------------------------------
 def decode_onehot(bits: np.ndarray, n: int, K: int) -> Tuple[np.ndarray, np.ndarray]:

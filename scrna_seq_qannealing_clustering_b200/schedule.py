@@ -166,10 +166,31 @@ def random_spin_states(num_reads: int, n: int, seed: int) -> np.ndarray:
     return values[rs.randint(0, 2, size=(num_reads, n))]
 
 
+def counter_spin_states(num_reads: int, n: int, seed: int, first_read: int = 0) -> np.ndarray:
+    """+-1 states from the library's counter-based generator (``qa_random_states``, csrc/postprocess.cuh::k_random_states):
+    spin (r, v) = bit (v & 63) of splitmix64-mix(seed, first_read + r, v >> 6), 1 -> -1.  A function of the GLOBAL read index:
+    any sharding of the reads over GPUs draws the same states, and the device draws them without a host copy
+    (``initial_states_generator='counter'``, an extension next to dimod's 'none' / 'tile' / 'random')."""
+    if num_reads * n == 0:
+        return np.empty((num_reads, n), dtype=np.int8)
+    words = (n + 63) // 64
+    r = np.arange(first_read, first_read + num_reads, dtype=np.uint64)[:, None]
+    w = np.arange(words, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + np.uint64(1)) * np.uint64(0xD1342543DE82EF95) + r * np.uint64(0x9E3779B97F4A7C15) \
+            + w * np.uint64(0xC2B2AE3D27D4EB4F)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    bits = np.unpackbits(z.view(np.uint8).reshape(num_reads, words, 8), axis=2, bitorder="little").reshape(num_reads, words * 64)
+    return np.ascontiguousarray(1 - 2 * bits[:, :n].astype(np.int8))
+
+
 def parse_initial_states(n: int, labels: Sequence, vartype_is_spin: bool, initial_states, initial_states_generator: str,
                          num_reads: Optional[int], seed: int) -> np.ndarray:
-    """dimod ``parse_initial_states`` for the three generators ('none', 'tile', 'random'); returns int8 +-1 [R][n]."""
-    if initial_states_generator not in ("none", "tile", "random"):
+    """dimod ``parse_initial_states`` for the three generators ('none', 'tile', 'random') plus the library's 'counter'
+    generator (random states as a function of the global read index); returns int8 +-1 [R][n]."""
+    if initial_states_generator not in ("none", "tile", "random", "counter"):
         raise ValueError("unknown value for 'initial_states_generator'")
     given = None
     if initial_states is not None:
@@ -203,6 +224,8 @@ def parse_initial_states(n: int, labels: Sequence, vartype_is_spin: bool, initia
     if given is None:
         if initial_states_generator == "none":
             raise ValueError("no initial states provided and 'initial_states_generator' is 'none'")
+        if initial_states_generator == "counter":
+            return counter_spin_states(num_reads, n, seed)
         return np.ascontiguousarray(random_spin_states(num_reads, n, seed))
     if len(given) > num_reads:
         given = given[:num_reads]

@@ -12,13 +12,13 @@ import pytest
 from oracle import oracle
 from scrna_seq_qannealing_clustering_b200 import _lib, models, schedule, snn
 
-RP_D, RP_SLOTS, RP_CAP = 16, 32, 448
+RP_D, RP_SLOTS, RP_CAP = 16, 64, 448
 RP_MAXBW = RP_SLOTS - 1
 HDR = np.dtype([("nent", "<i4"), ("nbw", "<i4"), ("v0", "<i4"), ("nv", "<i4"), ("prev_slot", "<i4"), ("seq_off", "<i4"),
                 ("nbw_next", "<i4"), ("pad", "<i4"), ("rowa", "<u4", RP_D), ("rowb", "<u4", RP_D), ("ga", "<i4", RP_D),
                 ("bw", "<i4", RP_SLOTS), ("bw_next", "<i4", RP_SLOTS)])
 ENT = np.dtype([("J", "<f8"), ("zero", "<u4"), ("B", "<u4")])
-assert HDR.itemsize == 480 and ENT.itemsize == 16
+assert HDR.itemsize == 736 and ENT.itemsize == 16
 
 
 def adjacency(n, starts, ends, weights):
@@ -99,17 +99,17 @@ def check_invariants(model, rows, blocks):
             early = sorted([(j, k) for k, (j, _) in enumerate(row) if j < v0])
             inblk = sorted([(j, k) for k, (j, _) in enumerate(row) if v0 <= j < u])
             pre, pad, seq = row_parts(hdr, ent, i)
-            assert [(int(e["B"]) >> 12, float(e["J"])) for e in pre] == [(j, row[k][1]) for j, k in later + early], f"row {u}: pre part"
-            assert [(int(e["B"]) >> 12, float(e["J"])) for e in seq] == [(j, row[k][1]) for j, k in inblk], f"row {u}: seq part"
+            assert [(int(e["B"]) >> 13, float(e["J"])) for e in pre] == [(j, row[k][1]) for j, k in later + early], f"row {u}: pre part"
+            assert [(int(e["B"]) >> 13, float(e["J"])) for e in seq] == [(j, row[k][1]) for j, k in inblk], f"row {u}: seq part"
             assert all(float(e["J"]) == 0.0 for e in pad) and len(pre) + len(pad) == 4 * (int(hdr["rowa"][i]) & 255)
             assert int(hdr["rowa"][i]) >> 16 == len(row) and (int(hdr["rowb"][i]) & 0xFFFF) == len(later)
             for e in list(pre) + list(seq):
-                j, B = int(e["B"]) >> 12, int(e["B"])
+                j, B = int(e["B"]) >> 13, int(e["B"])
                 assert int(e["zero"]) == 0 and (B & 31) == 30 - 2 * (j & 15)
-                slot = (B >> 7) & 31
+                slot = (B >> 7) & 63
                 assert (slot == 0 and (j >> 4) == own) or (slot > 0 and words[slot - 1] == (j >> 4))
             for e in pad:   # zero coupling: any readable slot will do
-                assert int(e["zero"]) == 0 and ((int(e["B"]) >> 7) & 31) == 0
+                assert int(e["zero"]) == 0 and ((int(e["B"]) >> 7) & 63) == 0
             total_pre += 4 * (int(hdr["rowa"][i]) & 255)
             if model.groups is not None and u < n and model.groups.grp[u] >= 0:
                 ga = int(hdr["ga"][i])
@@ -156,7 +156,7 @@ def replay_from_slabs(model, rows, blocks, state, betas, spb, seed):
                     pre, pad, _ = row_parts(hdr, ent, i)
                     acc = f[v0 + i] if v0 + i < n else 0.0
                     for e in list(pre) + list(pad):
-                        u = int(e["B"]) >> 12
+                        u = int(e["B"]) >> 13
                         sigma = (2.0 if sb[u] > 0 else -2.0) if Fb[u] else 0.0
                         acc = acc + float(e["J"]) * sigma
                     part.append(acc)
@@ -167,7 +167,7 @@ def replay_from_slabs(model, rows, blocks, state, betas, spb, seed):
                         break
                     fv = part[i]
                     for e in row_parts(hdr, ent, i)[2]:
-                        u = int(e["B"]) >> 12
+                        u = int(e["B"]) >> 13
                         if F[u]:
                             fv = fv + float(e["J"]) * (2.0 if s[u] > 0 else -2.0)
                     f[v] = fv
@@ -213,10 +213,22 @@ def test_four_way_model_packs_into_smaller_blocks():
     assert sizes.min() >= 1 and sizes.mean() >= 4
 
 
-def test_dense_and_scattered_models_are_rejected(graph256):
+def test_dense_models_are_rejected_and_scattered_ones_use_the_wide_slot_format(graph256):
     assert pack(models.cut_balance_model(graph256, 0.05, structured=False)) is None          # K_256: one variable per block
+    # 15 neighbours per cell scattered over 256 half-words: too many for 31 foreign slots, packs with 63 (smaller blocks)
     g = snn.synthetic_snn(4096, k=5, seed=1)[0]
-    assert pack(models.cut_linear_model(g, 0.01, 1.0)) is None   # 15 neighbours per cell scattered over 128 words
+    m = models.cut_linear_model(g, 0.01, 1.0)
+    rows, blocks, uniform = pack(m)
+    check_invariants(m, rows, blocks)
+    assert not uniform and max(int(h["nbw"]) for h, _ in blocks) > 31
+    # random graph of degree ~60: not even four rows share 63 half-words
+    rng = np.random.default_rng(5)
+    n = 4096
+    pairs = {(int(max(u, v)), int(min(u, v))) for u, v in rng.integers(0, n, size=(30 * n, 2)) if u != v}
+    pairs = sorted(pairs)
+    dense = models.LoweredModel(np.zeros(n), np.array([p[0] for p in pairs], dtype=np.int32), np.array([p[1] for p in pairs], dtype=np.int32),
+                                rng.normal(size=len(pairs)), 0.0, list(range(n)))
+    assert pack(dense) is None
 
 
 def test_shuffled_and_duplicated_couplers_keep_adjacency_order_among_ties():
