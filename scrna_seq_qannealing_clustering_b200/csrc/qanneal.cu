@@ -959,6 +959,9 @@ __global__ void __launch_bounds__(128) k_energy(const ProblemDesc *descs) {
     const uint32_t *pk = D.packedT + r;
     const int64_t stride = D.rpad;
     double E = 0.0;
+    // rank-1 group sums M_g = sum a_v s_v ride along with the linear pass (one pass over the spins for ALL groups)
+    long long M[QA_MAX_GROUPS];
+    for (int g = 0; g < D.ngroups; ++g) M[g] = 0;
     for (int c = 0; c < D.nch; ++c) {
         const uint32_t w = pk[c * stride];
         const int base = c * 32;
@@ -967,27 +970,41 @@ __global__ void __launch_bounds__(128) k_energy(const ProblemDesc *descs) {
             const double hv = __ldg(D.h + base + i);
             E += ((w >> i) & 1u) ? hv : -hv;  // state[v]*h[v]
         }
+        if (D.ngroups) {
+            for (int i = 0; i < lim; ++i) {
+                const int g = __ldg(D.grp + base + i);   // uniform
+                if (g >= 0) {
+                    const long long a = __ldg(D.coef + base + i);
+                    M[g] += ((w >> i) & 1u) ? a : -a;
+                }
+            }
+        }
     }
-    for (int64_t e = 0; e < D.m; ++e) {
+    // couplers in the caller's order: the additions are one dependent chain, the (random-row) spin loads are not -- issue
+    // them eight couplers at a time
+    int64_t e = 0;
+    for (; e + 8 <= D.m; e += 8) {
+        uint32_t bu[8], bv[8];
+        double wt[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int u = __ldg(D.starts + e + q), v = __ldg(D.ends + e + q);
+            wt[q] = __ldg(D.w + e + q);
+            bu[q] = pk[(int64_t)(u >> 5) * stride] >> (u & 31);
+            bv[q] = pk[(int64_t)(v >> 5) * stride] >> (v & 31);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) E += ((bu[q] ^ bv[q]) & 1u) ? -wt[q] : wt[q];  // state[u]*w*state[v]
+    }
+    for (; e < D.m; ++e) {
         const int u = __ldg(D.starts + e), v = __ldg(D.ends + e);
         const double wt = __ldg(D.w + e);
         const uint32_t bu = (pk[(int64_t)(u >> 5) * stride] >> (u & 31)) & 1u;
         const uint32_t bv = (pk[(int64_t)(v >> 5) * stride] >> (v & 31)) & 1u;
-        E += (bu ^ bv) ? -wt : wt;  // state[u]*w*state[v]
+        E += (bu ^ bv) ? -wt : wt;
     }
     for (int g = 0; g < D.ngroups; ++g) {
-        long long M = 0;
-        for (int c = 0; c < D.nch; ++c) {
-            const uint32_t w = pk[c * stride];
-            for (int i = 0; i < 32; ++i) {
-                const int v = c * 32 + i;
-                if (__ldg(D.grp + v) == g) {
-                    const long long a = __ldg(D.coef + v);
-                    M += ((w >> i) & 1u) ? a : -a;
-                }
-            }
-        }
-        const long long t = M + D.kappa[g];
+        const long long t = M[g] + D.kappa[g];
         E += D.lambda[g] * (double)(t * t) * 0.25;
     }
     D.energies[r] = E;
