@@ -399,6 +399,10 @@ def main():
         isel = torch.from_numpy(sel).to(dev)
         gpu_states = states_dev[isel].cpu().numpy()
         gpu_e = energies_dev[isel].cpu().numpy()
+        e_bad = np.flatnonzero(cpu_energies.view(np.uint64) != (gpu_e + model.offset).view(np.uint64))
+        if len(e_bad):   # say where and by how much (stderr; the JSON line carries the verdict)
+            print("[bench] energy mismatches at reads", sel[e_bad][:16].tolist(), "cpu", cpu_energies[e_bad][:4].tolist(),
+                  "gpu", (gpu_e + model.offset)[e_bad][:4].tolist(), file=sys.stderr)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
                "sample": f"{len(sel)} reads x {len(betas) * spb} sweeps x {n} vars of the same workload (head, middle and tail of the "
                          "wave), OpenMP over reads",

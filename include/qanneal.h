@@ -48,16 +48,20 @@ extern "C" {
 #define QA_SEED_STREAM 1     /* one xorshift128+ stream across reads == neal(num_reads=R, seed=seeds[0]) */
 /* mode */
 #define QA_MODE_REFERENCE 0  /* neal's sequential variable order, bit-exact against the oracle */
-#define QA_MODE_THROUGHPUT 1 /* neal's sequential sweep and per-read RNG, local fields re-evaluated from the spins at
-                               every attempt instead of updated incrementally: same algorithm, different fp64 rounding
-                               history -> not bit-exact, statistical parity; needs per-read seeding */
+#define QA_MODE_THROUGHPUT 1 /* tolerance-parity mode for DENSE models (qa_model_enable_dense): neal's sequential sweep and
+                               per-read RNG, local fields of every 8-cell block recomputed by fp64 tensor-core MMAs instead of
+                               updated incrementally: same algorithm, different fp64 rounding history -> energies to 1e-12
+                               relative, statistical parity.  Models without the dense form run the reference-order kernels
+                               (bit-exact) in this mode too */
 /* reference-mode kernel selection (both are bit-exact against the oracle) */
 #define QA_KERNEL_AUTO 0
 #define QA_KERNEL_WARP_PER_READ 1  /* one warp per read: any read count, stream seeding */
 #define QA_KERNEL_LOCKSTEP_PUSH 2  /* one warp per 32 reads, read-interleaved fields: many reads (>= ~10^4) */
-#define QA_KERNEL_LOCKSTEP_PULL 3  /* kernel behind QA_MODE_THROUGHPUT (not selectable in reference mode) */
+#define QA_KERNEL_LOCKSTEP_PULL 3  /* retired (round 2): the sparse recompute variant, overtaken by _REPLAY; never selected */
 #define QA_KERNEL_REPLAY 4         /* 32 reads per warp, deferred exact neighbour updates replayed at the visit; coupling
                                       slabs TMA-staged per CTA.  Sparse models; falls back to _LOCKSTEP_PUSH otherwise */
+#define QA_KERNEL_DENSE 5          /* QA_MODE_THROUGHPUT on a model with the dense k-way form (qa_model_enable_dense):
+                                      local fields of 8-cell blocks by fp64 tensor-core MMAs (DMMA) over all cells */
 
 #define QA_MAX_GROUPS 64
 
@@ -107,6 +111,13 @@ int qa_model_from_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, cons
  * (cut+balance, DQM cluster-size and CQM size penalties). grp[v] = -1: none. */
 int qa_model_set_groups(qa_model *model, int32_t ngroups, const int32_t *grp, const int32_t *coef,
                         const double *lambda, const int64_t *kappa);
+/* Dense k-way form (BASELINE config 5; the all-pairs same-case term of DQM_clustering.py:36-37 on a dense affinity):
+ * variable v = cell*K + case, J[(i,c),(j,c)] = W[i][j] for every case c, J[(i,c),(i,c')] = P.  Derives W (n/K x n/K) and P
+ * from the model's adjacency on the device and verifies the structure.  Returns 1 when the model has it -- QA_MODE_THROUGHPUT
+ * then anneals it with the tensor-core kernel (neal's sweep order and RNG, fields recomputed per block of 8 cells by
+ * mma.sync f64; energies to 1e-12 relative of neal's order) --, 0 when it does not (nothing changes).  K in {1, 2, 4, 8};
+ * K = 1 is a general dense Ising model. */
+int qa_model_enable_dense(qa_model *model, int32_t cases_per_cell);
 int qa_model_num_variables(const qa_model *model);
 int64_t qa_model_num_couplers(const qa_model *model);
 int qa_model_max_degree(const qa_model *model);
@@ -171,6 +182,42 @@ int qa_build_dqm_onehot(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *
 int qa_build_cqm_penalty(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
                          int32_t num_clusters, int32_t min_size, double onehot_penalty, double size_penalty, qa_model **out,
                          double *offset_out);
+
+/* ---- SNN graph construction on the device (the step before the path: Seurat FindNeighbors as the reference's notebooks use
+ * it, R/pbmc3k/Pbmc3k_general_data_preparation.Rmd:47-75, R/benchmarks/Benchmark.Rmd:150-166):
+ * exact kNN including self -> shared-neighbour counts s -> w = s/(2k - s) -> prune w < prune -> sequential symmetric degree
+ * trim to max_degree (<= 0: no trim).  num_problems independent point sets (points [point_offsets[p], point_offsets[p+1]) of
+ * X, row-major [total][dim], host or device) are built in the same launches.  Edges come out with u < v, local indices,
+ * sorted by (u, v) per problem -- identical to snn.py's graph.  The edge arrays stay on the device; qa_graph_device_edges
+ * hands them to the qa_build_* entry points without a host round trip. ---- */
+typedef struct qa_graph qa_graph;
+int qa_snn_build(qa_ctx *ctx, int32_t num_problems, const int64_t *point_offsets, int32_t dim, const double *X, int32_t k,
+                 double prune, int32_t max_degree, qa_graph **out);
+int64_t qa_graph_num_edges(const qa_graph *graph, int32_t problem);   /* problem < 0: all problems */
+int qa_graph_num_nodes(const qa_graph *graph, int32_t problem);
+int qa_graph_get_edges(const qa_graph *graph, int32_t problem, int32_t *eu, int32_t *ev, double *w);   /* copy out (any may be NULL) */
+int qa_graph_device_edges(const qa_graph *graph, int32_t problem, const int32_t **eu, const int32_t **ev, const double **w);
+int qa_graph_destroy(qa_graph *graph);
+
+/* ---- recursion driver on the device (the recursive calls of clustering_bqm / clustering_bqm_2 on G.subgraph(S0) and
+ * G.subgraph(S1), BQM_clustering.py:113-203, 302-350): all sub-graphs of a recursion level are extracted, built and annealed
+ * without a host / networkx round trip. ---- */
+/* G.subgraph(part) for every part at once: part[v] in [0, num_parts) or -1 (dropped).  Child p keeps the parent's node order
+ * (local index = rank inside the part) and the parent's edge order; edges with ends in different parts are dropped.
+ * Graph arrays and part may be host or device pointers.  The result is a qa_graph with num_parts problems. */
+int qa_graph_split(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
+                   const int32_t *part, int32_t num_parts, qa_graph **out);
+/* parent node of every node of child `problem` (problem < 0: all children back to back); host or device destination */
+int qa_graph_get_nodes(const qa_graph *graph, int32_t problem, int32_t *node_ids_out);
+/* single-problem models (rank-1 groups included) -> one batched model for qa_sa_sample_model_batch; the inputs stay valid and
+ * owned by the caller.  Batched models with groups run on the warp-per-read kernel. */
+int qa_model_concat(qa_ctx *ctx, int32_t num_models, qa_model *const *models, qa_model **out);
+/* qa_sa_sample_ising_batch on a resident batched model.  betas_per_problem = 0: beta_schedules is one schedule [num_betas] for
+ * every problem; 1: [num_problems][num_betas], problem p anneals with its own schedule (what separate sampler calls with
+ * default beta ranges would do). */
+int qa_sa_sample_model_batch(qa_ctx *ctx, qa_model *model, int32_t reads_per_problem, int8_t *states_inout, double *energies_out,
+                             int32_t num_betas, const double *beta_schedules, int32_t betas_per_problem, int32_t sweeps_per_beta,
+                             const uint64_t *seeds, qa_stats *stats_out);
 
 /* ---- SampleSet post-processing on the device (what the reference does with a SampleSet after the call:
  * energy-sorted iteration and k-th best energies BQM_clustering.py:93-146, the 16 best samples plot_and_save.py:105-126,

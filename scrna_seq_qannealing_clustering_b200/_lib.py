@@ -25,6 +25,7 @@ QA_KERNEL_WARP_PER_READ = 1
 QA_KERNEL_LOCKSTEP_PUSH = 2
 QA_KERNEL_LOCKSTEP_PULL = 3
 QA_KERNEL_REPLAY = 4
+QA_KERNEL_DENSE = 5
 QA_MAX_GROUPS = 64
 
 ERROR_NAMES = {
@@ -88,6 +89,7 @@ SIGNATURES = {
     "qa_ctx_last_kernel": (C.c_int, [_p]),
     "qa_model_from_ising": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p, C.POINTER(_p)]),
     "qa_model_set_groups": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
+    "qa_model_enable_dense": (C.c_int, [_p, _i32]),
     "qa_model_num_variables": (C.c_int, [_p]),
     "qa_model_num_couplers": (_i64, [_p]),
     "qa_model_max_degree": (C.c_int, [_p]),
@@ -108,6 +110,16 @@ SIGNATURES = {
     "qa_random_states": (C.c_int, [_p, C.c_uint64, _i64, _i32, _i32, _p]),
     "qa_argmin": (C.c_int, [_p, _i64, _p, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "qa_debug_pack_slabs": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "qa_snn_build": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, C.c_double, _i32, C.POINTER(_p)]),
+    "qa_graph_num_edges": (_i64, [_p, _i32]),
+    "qa_graph_num_nodes": (C.c_int, [_p, _i32]),
+    "qa_graph_get_edges": (C.c_int, [_p, _i32, _p, _p, _p]),
+    "qa_graph_device_edges": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "qa_graph_destroy": (C.c_int, [_p]),
+    "qa_graph_split": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _p, _i32, C.POINTER(_p)]),
+    "qa_graph_get_nodes": (C.c_int, [_p, _i32, _p]),
+    "qa_model_concat": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_p)]),
+    "qa_sa_sample_model_batch": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, C.POINTER(QAStats)]),
     "qa_sort_reads": (C.c_int, [_p, _i32, _p, _p]),
     "qa_gather_samples": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p]),
     "qa_decode_onehot": (C.c_int, [_p, _i32, _i32, _i64, _i32, _p, _i32, _i32, _p, _p]),

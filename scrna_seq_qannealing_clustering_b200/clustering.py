@@ -263,72 +263,107 @@ def disconnected_components(G):
 
 
 def recursive_bipartition_batched(G, gamma_factor, k=8.0, size_limit=40, iter_limit=2, num_reads=64, num_sweeps=200,
-                                  beta_range=None, seed=None, context=None, model="cut_balance"):
+                                  beta_range=None, seed=None, context=None, model="cut_balance", terminate_on="min_size",
+                                  write_labels=False):
     """Level-synchronous form of the recursion in ``clustering_bqm`` / ``clustering_bqm_2`` (BQM_clustering.py:113-203,
-    302-350, termination rule ``min_size``): instead of one sampler call per sub-graph, ALL sub-graphs of a recursion level
-    are annealed as one batch of independent problems in a single launch (``qa_sa_sample_ising_batch``, the launch behind
-    QA_subsampling's config 4).
+    302-350): instead of one sampler call per sub-graph, ALL sub-graphs of a recursion level are extracted, built and annealed
+    on the device as one batch of independent problems in a single launch (the launch behind QA_subsampling's config 4).
 
-    Every sub-graph gets the reference's model -- ``model="cut_balance"``: ``clustering_bqm``'s Q (k * cut + gamma * s(s - n),
-    materialised: the batched launch carries explicit couplers only, so this is meant for sub-graphs of up to a few thousand
-    cells); ``model="cut_linear"``: ``clustering_bqm_2``'s sparse Q (k * cut + gamma * sum x) -- ``num_reads`` reads with
-    per-read seeds and one beta schedule per level; its lowest-energy read splits it (``response.first``), and both halves go
-    to the next level while they are larger than ``size_limit`` and the level is below ``iter_limit``.
-    Returns ``{node: leaf index}``, the list of levels (each a list of node lists) and the per-level best energies.
-    """
+    Per level: ``qa_graph_split`` cuts the root graph into the level's sub-graphs on the device (``G.subgraph`` semantics: the
+    parent's node and edge order), ``qa_build_cut_balance`` builds each one's structured model (k * cut + gamma * s(s - n) with
+    the balance term as a rank-1 group -- ``model="cut_balance"``) or the host builder its sparse ``clustering_bqm_2`` model
+    (``model="cut_linear"``), ``qa_model_concat`` joins them and ``qa_sa_sample_model_batch`` anneals ``num_reads`` reads of
+    every problem, each with the beta schedule of ITS OWN default range unless ``beta_range`` is given.  Initial states and
+    per-read seeds are those a separate ``sampler.sample(model, seed=seed, num_reads=...)`` call per sub-graph would use, so
+    the tree equals the one ``clustering_bqm(..., sampler=B200SimulatedAnnealingSampler(), seed=seed)`` builds call by call
+    (tests/test_gpu_recursion.py).  Every termination rule of the reference is applied through ``bqm_rule`` / ``bqm2_rule``:
+    ``terminate_on`` in 'min_size', 'conf', 'once', 'iter_limit'.
+
+    Returns ``({node: leaf index}, levels, level_energies)``: ``levels[i]`` lists the node lists annealed at level i,
+    ``level_energies[i]`` their best energies.  ``write_labels=True`` also writes the reference's ``label<level>`` node
+    attributes (random colours) into ``G``."""
     from . import schedule
-    from .engine import Context
+    from .engine import Context, IsingModel
 
+    if model not in ("cut_balance", "cut_linear"):
+        raise ValueError("model must be 'cut_balance' or 'cut_linear'")
     own_ctx = context is None
     ctx = Context(0) if own_ctx else context
     try:
-        frontier = [list(G.nodes)]
+        labels, eu, ev, w = models.graph_arrays(G)
+        n_root = len(labels)
+        root = (n_root, eu.astype(np.int32), ev.astype(np.int32), w)
+        base_seed = schedule.resolve_seed(seed)
+        frontier = [np.arange(n_root, dtype=np.int64)]
         leaves, levels, level_energies = [], [], []
         iteration = 0
-        rng_seed = 0 if seed is None else int(seed)
         while frontier:
-            levels.append(frontier)
-            if model == "cut_balance":
-                ms = [models.cut_balance_model(G.subgraph(nodes), gamma_factor, k=k, structured=False) for nodes in frontier]
-            elif model == "cut_linear":
-                ms = [models.cut_linear_model(G.subgraph(nodes), gamma_factor, k) for nodes in frontier]
-            else:
-                raise ValueError("model must be 'cut_balance' or 'cut_linear'")
-            br = beta_range
-            if br is None:   # one schedule for the whole level: the widest range any of its problems asks for
-                rs = [schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights) for m in ms if m.num_couplers > 0]
-                br = (min(r[0] for r in rs), max(r[1] for r in rs)) if rs else (0.1, 1.0)
-            betas, spb = schedule.make_beta_schedule(br, num_sweeps, 1, "geometric")
-            voff = np.cumsum([0] + [m.num_variables for m in ms])
-            coff = np.cumsum([0] + [m.num_couplers for m in ms])
-            seeds = schedule.per_read_seeds(rng_seed + 7919 * iteration, num_reads * len(ms))
-            states = np.concatenate([schedule.random_spin_states(num_reads, m.num_variables, rng_seed + 31 * iteration + i).ravel()
-                                     for i, m in enumerate(ms)])
-            e, _, done = ctx.sample_ising_batch(voff, coff, np.concatenate([m.h for m in ms]),
-                                                np.concatenate([m.starts for m in ms]), np.concatenate([m.ends for m in ms]),
-                                                np.concatenate([m.weights for m in ms]), num_reads, states, betas, spb, seeds)
-            assert done == num_reads
+            levels.append([[labels[i] for i in part] for part in frontier])
+            P = len(frontier)
+            part_of = np.full(n_root, -1, dtype=np.int32)
+            for p, part in enumerate(frontier):
+                part_of[part] = p
+            dg = ctx.split_graph(root, part_of, P)
+            gms, offsets = [], []
+            try:
+                for p in range(P):
+                    if model == "cut_balance":
+                        gm, off, _ = ctx.build_cut_balance(dg.device_graph(p), gamma_factor, k)
+                    else:
+                        hm = models.cut_linear_model(dg.graph(p), gamma_factor, k)
+                        gm, off = IsingModel(ctx, hm.h, hm.starts, hm.ends, hm.weights), hm.offset
+                    gms.append(gm)
+                    offsets.append(off)
+                if beta_range is None:   # every problem the default range of its own vectors, as separate sampler calls would
+                    sched = [schedule.make_beta_schedule(schedule.default_ising_beta_range(*gm.get_ising(), None), num_sweeps, 1,
+                                                         "geometric") for gm in gms]
+                    betas, spb = np.stack([b for b, _ in sched]), sched[0][1]
+                else:
+                    betas, spb = schedule.make_beta_schedule(beta_range, num_sweeps, 1, "geometric")
+                sizes = [gm.num_variables for gm in gms]
+                states = np.concatenate([schedule.random_spin_states(num_reads, nv, base_seed).ravel() for nv in sizes])
+                seeds = np.tile(schedule.per_read_seeds(base_seed, num_reads), P)
+                bm = ctx.concat_models(gms)
+                try:
+                    e, _, done = ctx.sample_model_batch(bm, num_reads, states, betas, spb, seeds)
+                finally:
+                    bm.close()
+                assert done == num_reads
+            finally:
+                for gm in gms:
+                    gm.close()
+                dg.close()
             nxt, best = [], []
             off = 0
-            for i, (nodes, m) in enumerate(zip(frontier, ms)):
-                n = m.num_variables
-                rows = states[off:off + num_reads * n].reshape(num_reads, n)
-                off += num_reads * n
-                ei = e[i * num_reads:(i + 1) * num_reads]
-                b = int(np.argmin(ei))          # first minimum == SampleSet.first of an energy-sorted, stable record
-                best.append(float(ei[b] + m.offset))
-                S0 = [lab for lab, s in zip(m.labels, rows[b]) if s < 0]     # x = 0
-                S1 = [lab for lab, s in zip(m.labels, rows[b]) if s > 0]     # x = 1
-                go = len(S0) > size_limit and len(S1) > size_limit and iteration < iter_limit
-                for part in (S0, S1):
-                    if not part:
-                        continue
-                    (nxt if go else leaves).append(part)
+            for p, part in enumerate(frontier):
+                nv = sizes[p]
+                rows = states[off:off + num_reads * nv].reshape(num_reads, nv)
+                off += num_reads * nv
+                ep = e[p * num_reads:(p + 1) * num_reads] + offsets[p]
+                b = int(np.argmin(ep))          # first minimum == SampleSet.first of an energy-sorted, stable record
+                best.append(float(ep[b]))
+                S0, S1 = part[rows[b] < 0], part[rows[b] > 0]          # x = 0 / x = 1
+                if model == "cut_balance":
+                    go, how = bqm_rule(terminate_on, len(S0), len(S1), np.sort(ep, kind="stable"), iteration, size_limit, iter_limit)
+                    # the reference's conf branch labels the halves, recurses, then overwrites the level with one colour
+                    shown = "split" if (go and terminate_on != "conf") else how
+                else:
+                    go, how = bqm2_rule(terminate_on, len(S0), len(S1), np.sort(ep, kind="stable"), size_limit)
+                    shown = how
+                if write_labels and shown is not None:
+                    sub = G.subgraph([labels[i] for i in part])
+                    _write_labels(sub, [labels[i] for i in S0], [labels[i] for i in S1], "label" + str(iteration), shown, 20 * iteration)
+                if go:
+                    nxt.extend(x for x in (S0, S1) if len(x))
+                elif how in ("split", "color"):
+                    leaves.extend(x for x in (S0, S1) if len(x))
+                else:
+                    leaves.append(part)
             level_energies.append(best)
             frontier = nxt
             iteration += 1
-        labels = {node: idx for idx, part in enumerate(leaves) for node in part}
-        return labels, levels, level_energies
+        out = {labels[i]: idx for idx, part in enumerate(leaves) for i in part}
+        return out, levels, level_energies
     finally:
         if own_ctx:
             ctx.close()

@@ -94,6 +94,7 @@ struct ProblemDesc {
     const uint32_t *rp_off;         // [rp_nslabs + 1] slab offsets of this problem in 16-byte units
     int32_t rp_nslabs;              // blocks (slabs) of this problem
     int32_t pad2_;
+    const double *betas;            // this problem's own beta schedule [num_betas], or null: the launch's shared schedule
 };
 
 struct AnnealParams {
@@ -129,6 +130,9 @@ struct AnnealParams {
     int32_t switch_permille;     // replay -> push hand-over: CTA-wide acceptance of a sweep below this many per mille
     int32_t rp_slab_init;        // adjacency lists ascending: the field set-up pass runs through the slab ring
     const int *interrupt_flag;   // host-mapped flag (or null): CTAs stop pulling work once it is non-zero
+    // dense k-way kernel (dense.cuh)
+    uint32_t *dn_spins;          // [slots][dn_stride] bit-packed spins, one slot per resident warp
+    int64_t dn_stride;           // (ncp / 32) * 32 * K words
 };
 
 enum { ST_CAND = 0, ST_DRAWS, ST_ACC, ST_NBR, ST_ACTIVE, ST_CHUNKS, ST_TIES, QA_NSTAT };
@@ -232,7 +236,7 @@ __device__ void anneal_read(const ProblemDesc &D, const AnnealParams &P, int64_t
 
     // ---- the anneal: for beta: for sweep: for var (neal order)
     for (int b = 0; b < P.num_betas; ++b) {
-        const double beta = P.betas[b];
+        const double beta = (D.betas ? D.betas : P.betas)[b];
         const double thr = 44.36142 / beta;
         for (int sw = 0; sw < P.sweeps_per_beta; ++sw) {
             uint32_t wg = 0;
@@ -420,9 +424,11 @@ __global__ void __launch_bounds__(QA_TPB_MAX, 4) k_anneal_ref(AnnealParams P) {
 // instead of 32 scattered 8-byte ones, and exp()/RNG run on all lanes at once.
 //   VARIANT 0 "push": local fields f[v][lane] (fp64, read-interleaved) are kept in HBM and updated by
 //                     red.global.add.f64 exactly like the warp-per-read kernel -> bit-exact against the oracle.
-//   VARIANT 1 "pull": no field state at all; f[v] = h_v + sum_j J_vj s_j is re-evaluated from the bit-packed
-//                     spins at every attempt (neal's algorithm, sequential variable order, per-read RNG, but the
-//                     fp64 rounding history of the fields differs) -> throughput mode, statistical parity.
+//   VARIANT 2 "init": one pass that evaluates f[v] = h_v + sum_j J_vj s_j from the bit-packed spins through per-block
+//                     tables of distinct spin words (neal's get_flip_energy order) -- the set-up of the push variant.
+//   (A former VARIANT 1 re-evaluated the fields at every attempt as a non-bit-exact throughput mode for sparse models; the
+//   exact replay kernel overtook it and it was retired, DESIGN.md 4.4.  QA_MODE_THROUGHPUT now means the dense tensor-core
+//   kernel of dense.cuh.)
 // Spins live in the read-transposed packed layout packedT[word][read] the energy kernel consumes.
 // ------------------------------------------------------------------------------------------------
 constexpr int QA_LS_TPB = 128;   // threads per block of the lockstep kernels
@@ -431,7 +437,6 @@ constexpr int QA_LS_D = 16;      // variables per staged block
 constexpr int QA_LS_CAP = 384;   // CSR entries staged per block (longer blocks fall back to global loads)
 constexpr int QA_LS_CAPW = 32;   // distinct spin words per block held in shared memory (aliases the `cur` staging area)
 static_assert(QA_LS_CAPW * sizeof(uint32_t) <= QA_LS_D * sizeof(double), "spin-word staging must fit into the field staging area");
-constexpr int QA_SWITCH_PERMILLE = 30;  // throughput mode: pull while > 3 % of the attempts of a sweep are accepted
 
 struct LaneStats {
     unsigned int cand, draws, acc, ties;
@@ -540,10 +545,8 @@ __device__ __forceinline__ double ls_field_direct(const ProblemDesc &D, const ui
     return fv;
 }
 
-// Runs sweeps from (bi, swi) on; returns true when the schedule is finished, false when the pull variant hands over to
-// the push variant (bi, swi then name the next sweep).  VARIANT 0 = push (bit-exact), 1 = pull (recomputed fields),
-// 2 = one pass that only evaluates the local fields from the spins and stores them (neal get_flip_energy order): the
-// initialisation of the push variant, run through the same staged pipeline as the pull variant.
+// Runs the schedule from (bi, swi) on.  VARIANT 0 = push sweeps (bit-exact), 2 = one pass that only evaluates the local fields
+// from the spins and stores them (neal get_flip_energy order): the initialisation of the push variant.
 template <int VARIANT, bool GROUPS>
 __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, unsigned long long &s0,
                           unsigned long long &s1, LaneStats &st) {
@@ -562,7 +565,6 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
     const bool active = c.active;
     const bool tables = VARIANT >= 1 && D.bw_ptr != nullptr;
     const int nblk = nch * (32 / QA_LS_D);
-    const unsigned nactive = __popc(__ballot_sync(FULL_MASK, active));
 
     // software pipeline over blocks of QA_LS_D variables:
     //   rows (and, for pull, h / slot bytes / distinct-word list) of block b+1 are copied to shared memory by cp.async while
@@ -624,12 +626,11 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
     const int nbeta = VARIANT == 2 ? 1 : P.num_betas;
     const int nspb = VARIANT == 2 ? 1 : P.sweeps_per_beta;
     for (; bi < nbeta; ++bi, swi = 0) {
-        const double beta = VARIANT == 2 ? 1.0 : P.betas[bi];
+        const double beta = VARIANT == 2 ? 1.0 : (D.betas ? D.betas : P.betas)[bi];
         const double thr = 44.36142 / beta;
         for (; swi < nspb; ++swi) {
             uint32_t w = 0;
             bool dirty = false;
-            unsigned sweep_acc = 0;
             for (int blk = 0; blk < nblk; ++blk) {
                 const int v0 = blk * QA_LS_D;
                 const int wi = v0 >> 5;
@@ -734,7 +735,6 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                     const bool acc = ls_accept(dE, cand, beta, s0, s1, st);
                     const unsigned accm = __ballot_sync(FULL_MASK, acc);
                     if (accm == 0) continue;
-                    sweep_acc += __popc(accm);
                     if (acc) {
                         st.acc++;
                         st.nbr += (unsigned long long)(e1 - e0);
@@ -799,27 +799,13 @@ __device__ bool ls_sweeps(const LsCtx &c, int &bi, int &swi, bool allow_switch, 
                 rp_nxt = rp_nn; gm_nxt = gm_nn; am_nxt = am_nn;
                 parity ^= 1;
             }
-            if (VARIANT == 1) {
-                // hand over to the push variant once flips are rare (uniform decision: warp-wide count of this sweep)
-                if (allow_switch && (unsigned long long)sweep_acc * 1000ull < (unsigned long long)QA_SWITCH_PERMILLE * n * nactive) {
-                    ++swi;
-                    finished = false;
-                    goto done;
-                }
-            }
         }
     }
-done:
     cp_async_wait<0>();
     __syncwarp();
-    if (!finished && swi >= P.sweeps_per_beta) {
-        swi = 0;
-        ++bi;
-    }
-    return finished && true;
+    return finished;
 }
 
-// VARIANT 0: push only (reference mode).  VARIANT 1: throughput mode = pull while flips are frequent, then push.
 template <int VARIANT, bool GROUPS>
 __device__ void lockstep_tile(const LsCtx &c, unsigned long long &s0, unsigned long long &s1, LaneStats &st, int *error_flag) {
     const ProblemDesc &D = c.D;
@@ -859,7 +845,6 @@ __device__ void lockstep_tile(const LsCtx &c, unsigned long long &s0, unsigned l
     }
     int bi = 0, swi = 0;
     bool finished = false;
-    if (VARIANT == 1) finished = ls_sweeps<1, GROUPS>(c, bi, swi, c.fT != nullptr, s0, s1, st);
     if (!finished) {
         int ib = 0, is = 0;
         ls_sweeps<2, false>(c, ib, is, false, s0, s1, st);  // local fields from the current spins
@@ -948,6 +933,7 @@ __global__ void __launch_bounds__(QA_LS_TPB, 3) k_anneal_lockstep(AnnealParams P
 }
 
 #include "replay.cuh"
+#include "dense.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // energies: neal get_state_energy(), one thread per read, reads on lanes (coalesced packedT loads)
@@ -1253,6 +1239,7 @@ struct qa_ctx {
     int last_kernel = 0;              // QA_KERNEL_* the last sampling call ran on
     unsigned rp_smem_base = 1024;     // shared-window offset of dynamic shared memory (verified by the replay kernel)
     bool rp_base_checked = false;
+    bool betas_per_problem = false;   // transient: the running call carries one beta schedule per problem ([P][num_betas])
     int *h_iflag = nullptr, *d_iflag = nullptr;  // host-mapped interrupt flag polled by the replay kernel
     unsigned long long *d_stats = nullptr;  // QA_NSTAT counters + 1 read counter
     int *d_flag = nullptr;
@@ -1293,6 +1280,10 @@ struct qa_model {
     int rp_slots = 32;         // half-word slots per warp the slabs were packed for (32 or 64)
     bool rp_adj_sorted = false; // adjacency lists ascending: field set-up through the slab ring
     bool groups_i32 = false;   // every group term a*(a - s*(M+kappa)) fits 32-bit integers
+    // dense k-way form (dense.cuh): W and P derived from the CSR by qa_model_enable_dense
+    double *dn_W = nullptr;
+    bool dn_ok = false;
+    DenseDesc dn = {};
 };
 
 namespace {
@@ -1422,6 +1413,7 @@ int finalize_descs(qa_model *M) {
         D.grp = nullptr; D.coef = nullptr; D.lambda = nullptr; D.kappa = nullptr;
         D.bw_ptr = nullptr; D.bw_words = nullptr; D.ent_slot = nullptr;
         D.rp_slabs = nullptr; D.rp_off = nullptr; D.rp_nslabs = 0;
+        D.betas = nullptr;
         M->n_max = std::max(M->n_max, D.n);
     }
     M->nch_max = (M->n_max + 31) / 32;
@@ -1781,6 +1773,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
             D.states = d_states + st_off;
             D.packedT = (uint32_t *)ctx->packed.p + off;
             D.energies = d_energies + (int64_t)p * reads_per_problem;
+            D.betas = ctx->betas_per_problem ? d_betas + (int64_t)p * num_betas : nullptr;
             off += (size_t)D.nch * rpad;
             st_off += (int64_t)reads_per_problem * D.n;
         }
@@ -1789,21 +1782,25 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
 
     const bool groups = M->ngroups > 0;
     // kernel choice: warp-per-read (any read count, stream seeding) or lockstep (32 reads per warp)
+    // QA_MODE_THROUGHPUT: a model with the dense k-way form runs the tensor-core kernel (tolerance parity); every other model
+    // runs the reference-order kernels below -- for sparse models the exact replay kernel is faster than any recompute or
+    // graph-coloured update, and bit-exact results meet the statistical bar trivially
     int kernel = QA_KERNEL_WARP_PER_READ;
-    if (mode == QA_MODE_THROUGHPUT) kernel = QA_KERNEL_LOCKSTEP_PULL;
+    if (mode == QA_MODE_THROUGHPUT && M->dn_ok && P == 1 && !interrupt && seed_mode == QA_SEED_PER_READ) kernel = QA_KERNEL_DENSE;
     else if (ctx->kernel == QA_KERNEL_LOCKSTEP_PUSH && seed_mode == QA_SEED_PER_READ) kernel = QA_KERNEL_LOCKSTEP_PUSH;
     else if (ctx->kernel == QA_KERNEL_AUTO && seed_mode == QA_SEED_PER_READ && (int64_t)reads_per_problem >= 32 &&
              2 * total_reads >= (int64_t)ctx->num_sms * 32 * 7)
         kernel = QA_KERNEL_LOCKSTEP_PUSH;
-    if (kernel == QA_KERNEL_LOCKSTEP_PULL && seed_mode != QA_SEED_PER_READ)
-        return fail(QA_ERR_ARG, "throughput mode needs per-read seeding");
     // replay kernel (deferred exact updates): sparse models whose blocks fit the slab format; explicit choice, or automatic
     // from 6144 reads on (measured on B200, config 3: 1.26e10 vs 7.5e9 attempts/s for the warp-per-read kernel at 12 500
     // reads, 4.3e9 vs 5.9e9 at 4096)
     // an interrupt callback: the warp-per-read kernel runs in read waves and polls between them; the replay kernel polls a
     // host-mapped flag whenever a CTA pulls its next group of reads; the lockstep push kernel has no stopping point
     if (interrupt && kernel == QA_KERNEL_LOCKSTEP_PUSH) kernel = QA_KERNEL_WARP_PER_READ;
-    if (mode == QA_MODE_REFERENCE && seed_mode == QA_SEED_PER_READ && (!interrupt || P == 1) &&
+    // batched models with rank-1 groups (qa_model_concat): the lockstep and replay kernels keep one copy of lambda / kappa per
+    // CTA, so those run on the warp-per-read kernel, which reads them per problem
+    if (P > 1 && groups) kernel = QA_KERNEL_WARP_PER_READ;
+    if (kernel != QA_KERNEL_DENSE && seed_mode == QA_SEED_PER_READ && (!interrupt || P == 1) && !(P > 1 && groups) &&
         (ctx->kernel == QA_KERNEL_REPLAY ||
          (ctx->kernel == QA_KERNEL_AUTO && (int64_t)reads_per_problem >= 32 && total_reads >= 6144))) {
         rc = build_replay_tables(M);
@@ -1880,6 +1877,37 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
                 if (interrupt(iuser)) { interrupted = true; break; }
             }
         }
+    } else if (kernel == QA_KERNEL_DENSE) {
+        // dense k-way: one warp = 32 reads, fields of a block of 8 cells by fp64 tensor-core MMAs over all cells (dense.cuh)
+        const int K = M->dn.K;
+        const int warps = 4;
+        const void *fn = K == 1 ? (const void *)k_anneal_dense<1> : K == 2 ? (const void *)k_anneal_dense<2>
+                       : K == 4 ? (const void *)k_anneal_dense<4> : (const void *)k_anneal_dense<8>;
+        const size_t smem = K == 1 ? dn_smem_bytes<1>(warps) : K == 2 ? dn_smem_bytes<2>(warps)
+                          : K == 4 ? dn_smem_bytes<4>(warps) : dn_smem_bytes<8>(warps);
+        QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int bps = 0;
+        QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, warps * 32, smem, cudaOccupancyDefault));
+        if (bps < 1) return fail(QA_ERR_CUDA, "dense kernel does not fit on an SM");
+        const int64_t total_tiles = (reads_per_problem + 31) / 32;
+        // few tiles: one warp per CTA on as many SMs as there are tiles (idle warps leave at once)
+        const int64_t grid = std::min<int64_t>((int64_t)bps * ctx->num_sms, total_tiles);
+        const int64_t stride = (int64_t)M->dn.ngrp * 32 * K;
+        rc = ensure(ctx->sf, (size_t)grid * warps * stride * sizeof(uint32_t));
+        if (rc) return rc;
+        A.dn_spins = (uint32_t *)ctx->sf.p;
+        A.dn_stride = stride;
+        A.total_tiles = total_tiles;
+        A.read_begin = 0;
+        A.read_end = total_reads;
+        QA_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+        QA_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), ctx->stream));
+        void *args[] = {&A, &M->dn};
+        QA_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, ctx->stream));
+        QA_CUDA(cudaGetLastError());
+        ctx->launches++;
+        if (st) st->anneal_launches++;
+        done = total_reads;
     } else if (kernel == QA_KERNEL_REPLAY) {
         // replay: one CTA = `nw` consecutive 32-read tiles of one problem, coupling slabs shared through a TMA ring
         const int tpp = (reads_per_problem + 31) / 32;
@@ -1986,13 +2014,11 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         }
     } else {
         // lockstep: one warp = 32 reads of one problem
-        const bool pull = kernel == QA_KERNEL_LOCKSTEP_PULL;
         const int tpp = (reads_per_problem + 31) / 32;
         const int64_t total_tiles = (int64_t)P * tpp;
         const size_t smem = ls_smem_bytes(std::max(M->ngroups, 1));
         const void *fn = nullptr;
-        if (!pull) fn = groups ? (const void *)k_anneal_lockstep<0, true> : (const void *)k_anneal_lockstep<0, false>;
-        else fn = groups ? (const void *)k_anneal_lockstep<1, true> : (const void *)k_anneal_lockstep<1, false>;
+        fn = groups ? (const void *)k_anneal_lockstep<0, true> : (const void *)k_anneal_lockstep<0, false>;
         QA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int bps = 0;
         QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, QA_LS_TPB, smem, cudaOccupancyDefault));
@@ -2010,15 +2036,11 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
             const size_t per_slot = (size_t)fT_stride * sizeof(double);
             const size_t budget = (size_t)((double)(free_b + ctx->fT.bytes) * 0.85);
             int64_t max_slots = (int64_t)(budget / per_slot);
-            if (max_slots < wpb) {
-                if (!pull) return fail(QA_ERR_CUDA, "not enough device memory for one block of local fields");
-                A.fT_scratch = nullptr;  // throughput mode then recomputes fields for the whole schedule
-            } else {
-                if (grid * wpb > max_slots) grid = max_slots / wpb;
-                rc = ensure(ctx->fT, (size_t)grid * wpb * per_slot);
-                if (rc) return rc;
-                A.fT_scratch = (double *)ctx->fT.p;
-            }
+            if (max_slots < wpb) return fail(QA_ERR_CUDA, "not enough device memory for one block of local fields");
+            if (grid * wpb > max_slots) grid = max_slots / wpb;
+            rc = ensure(ctx->fT, (size_t)grid * wpb * per_slot);
+            if (rc) return rc;
+            A.fT_scratch = (double *)ctx->fT.p;
         }
         rc = build_word_tables(M);  // field evaluation from spins (init pass of push, pull variant) runs on these
         if (rc) return rc;
@@ -2039,7 +2061,7 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         done = total_reads;
     }
     QA_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    {
+    if (kernel != QA_KERNEL_DENSE) {   // the dense kernel evaluates the energies itself (one more field pass)
         dim3 g((unsigned)((reads_per_problem + 127) / 128), (unsigned)P);
         k_energy<<<g, 128, 0, ctx->stream>>>(M->d_descs);
         QA_CUDA(cudaGetLastError());
@@ -2125,9 +2147,10 @@ int sample_common(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *s
     }
     const double *d_betas = beta_schedule;
     if (num_betas > 0 && !is_device_ptr(beta_schedule)) {
-        rc = ensure(ctx->betas, (size_t)num_betas * sizeof(double));
+        const size_t nb = (size_t)num_betas * (ctx->betas_per_problem ? (size_t)M->num_problems : 1);
+        rc = ensure(ctx->betas, nb * sizeof(double));
         if (rc) return rc;
-        QA_CUDA(cudaMemcpyAsync(ctx->betas.p, beta_schedule, (size_t)num_betas * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        QA_CUDA(cudaMemcpyAsync(ctx->betas.p, beta_schedule, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         d_betas = (const double *)ctx->betas.p;
     }
     QA_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -2268,6 +2291,7 @@ int qa_model_set_groups(qa_model *M, int32_t ngroups, const int32_t *grp, const 
     if (M->lambda) { cudaFree(M->lambda); M->lambda = nullptr; }
     if (M->kappa) { cudaFree(M->kappa); M->kappa = nullptr; }
     M->ngroups = ngroups;
+    if (ngroups > 0) M->dn_ok = false;   // the dense form carries no group terms
     if (M->rp_slabs) { cudaFree(M->rp_slabs); M->rp_slabs = nullptr; }   // the slabs carry the group metadata
     if (M->rp_off) { cudaFree(M->rp_off); M->rp_off = nullptr; }
     M->rp_built = false;
@@ -2317,6 +2341,73 @@ int qa_model_set_groups(qa_model *M, int32_t ngroups, const int32_t *grp, const 
     return QA_OK;
 }
 
+// Dense k-way form for k_anneal_dense: W[i][j] = J between (i,c) and (j,c), P = J between two cases of one cell, derived
+// from the device CSR and verified (every inter-cell coupler joins equal cases and does not depend on the case, every
+// intra-cell coupler equals P).  Returns 1 when the model has that structure (QA_MODE_THROUGHPUT then runs the
+// tensor-core kernel), 0 when it does not (nothing changes).
+int qa_model_enable_dense(qa_model *M, int32_t K) {
+    if (!M) return fail(QA_ERR_ARG, "null model");
+    if (K != 1 && K != 2 && K != 4 && K != 8) return fail(QA_ERR_ARG, "dense form: cases per cell must be 1, 2, 4 or 8");
+    if (M->num_problems != 1 || M->ngroups != 0) return fail(QA_ERR_ARG, "dense form needs a single problem without groups");
+    const int64_t n = M->n_total;
+    if (n == 0 || n % K != 0) return fail(QA_ERR_ARG, "number of variables is not a multiple of the cases per cell");
+    qa_ctx *ctx = M->ctx;
+    QA_CUDA(cudaSetDevice(ctx->device));
+    if (M->dn_W) { cudaFree(M->dn_W); M->dn_W = nullptr; }
+    M->dn_ok = false;
+    const int32_t ncells = (int32_t)(n / K);
+    const int32_t ncp = (ncells + 31) & ~31;
+    // P: the first intra-cell coupler of variable 0 (its neighbours 1..K-1 come first in an ascending row; any order works)
+    double Pj = 0.0;
+    if (K > 1) {
+        int32_t rp[2];
+        QA_CUDA(cudaMemcpy(rp, M->rowptr, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        const int32_t d0 = rp[1] - rp[0];
+        if (d0 > 0) {
+            std::vector<int32_t> c0(d0);
+            std::vector<double> v0(d0);
+            QA_CUDA(cudaMemcpy(c0.data(), M->col + rp[0], (size_t)d0 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            QA_CUDA(cudaMemcpy(v0.data(), M->val + rp[0], (size_t)d0 * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int32_t e = 0; e < d0; ++e)
+                if (c0[e] < K) { Pj = v0[e]; break; }
+        }
+    }
+    const size_t cells2 = (size_t)ncp * ncp;
+    QA_CUDA(cudaMalloc((void **)&M->dn_W, cells2 * sizeof(double)));
+    unsigned long long *Wb = reinterpret_cast<unsigned long long *>(M->dn_W);
+    unsigned long long *d_counts = nullptr;
+    QA_CUDA(cudaMalloc((void **)&d_counts, 2 * sizeof(unsigned long long)));
+    QA_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    QA_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
+    const int tpb = 256;
+    k_dense_fill<<<(unsigned)((cells2 + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(cells2, Wb);
+    for (int pass = 0; pass < 2; ++pass)
+        k_dense_scatter<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, ctx->stream>>>((int32_t)n, K, ncp, M->rowptr, M->col, M->val, Pj, Wb,
+                                                                                 ctx->d_flag, d_counts, pass);
+    k_dense_finish<<<(unsigned)((cells2 + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(cells2, Wb);
+    ctx->launches += 4;
+    int flag = 0;
+    unsigned long long counts[2] = {0, 0};
+    cudaError_t ce = cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_counts);
+    if (ce != cudaSuccess) return fail(QA_ERR_CUDA, std::string("dense form: ") + cudaGetErrorString(ce));
+    if (flag != 0 || counts[0] * (unsigned long long)K != counts[1]) {
+        cudaFree(M->dn_W);
+        M->dn_W = nullptr;
+        return 0;
+    }
+    M->dn.ncells = ncells;
+    M->dn.ncp = ncp;
+    M->dn.K = K;
+    M->dn.ngrp = ncp / 32;
+    M->dn.W = M->dn_W;
+    M->dn.P = Pj;
+    M->dn_ok = true;
+    return 1;
+}
+
 int qa_model_num_variables(const qa_model *M) { return M ? (int)M->n_total : fail(QA_ERR_ARG, "null model"); }
 int64_t qa_model_num_couplers(const qa_model *M) { return M ? M->m_total : (int64_t)fail(QA_ERR_ARG, "null model"); }
 int qa_model_max_degree(const qa_model *M) { return M ? M->max_deg : fail(QA_ERR_ARG, "null model"); }
@@ -2336,7 +2427,7 @@ int qa_model_destroy(qa_model *M) {
     cudaSetDevice(M->ctx->device);
     cudaStreamSynchronize(M->ctx->stream);
     void *ptrs[] = {M->h, M->starts, M->ends, M->w, M->rowptr, M->col, M->val, M->grp, M->coef, M->lambda, M->kappa, M->d_descs,
-                    M->bw_ptr, M->bw_words, M->ent_slot, M->rp_slabs, M->rp_off};
+                    M->bw_ptr, M->bw_words, M->ent_slot, M->rp_slabs, M->rp_off, M->dn_W};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete M;
     return QA_OK;
@@ -2787,3 +2878,5 @@ int qa_build_dqm_onehot(qa_ctx *ctx, int32_t n, int64_t m, const int32_t *eu, co
 }  // extern "C"
 
 #include "postprocess.cuh"
+#include "snn.cuh"
+#include "recursion.cuh"

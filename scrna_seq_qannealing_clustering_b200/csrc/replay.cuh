@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_repla
         bool push = false;
         long long done = 0;
         for (int bi = 0; bi < P.num_betas; ++bi) {
-            const double beta = P.betas[bi];
+            const double beta = (D.betas ? D.betas : P.betas)[bi];
             for (int swi = 0; swi < P.sweeps_per_beta; ++swi) {
                 ++done;
                 const bool more = done < total_sweeps;

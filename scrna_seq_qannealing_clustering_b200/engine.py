@@ -173,9 +173,69 @@ class Context:
         check(_lib.load().qa_argmin(self._h, count, ptr(values), C.byref(bv), C.byref(bi)))
         return float(bv.value), int(bi.value)
 
+    # -- SNN graphs on the device (qa_snn_build): the step before the path ------------------------
+    def build_snn(self, X, k: int = 5, prune: float = 1.0 / 15.0, max_degree: Optional[int] = 15, offsets=None) -> "DeviceGraph":
+        """Seurat-style SNN graph(s) of the rows of ``X`` ([points][dim] fp64, host array or device tensor) built by the
+        ``k_snn_*`` kernels (R/pbmc3k/Pbmc3k_general_data_preparation.Rmd:47-75): identical to ``snn.snn_graph``.  ``offsets``
+        ([P + 1]) splits the rows into P independent point sets, each with its own graph (config 4)."""
+        if not _is_tensor(X):
+            X = np.ascontiguousarray(X, dtype=np.float64)
+        total, dim = int(X.shape[0]), int(X.shape[1])
+        off = np.array([0, total], dtype=np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        if off[0] != 0 or off[-1] != total:
+            raise ValueError("offsets must start at 0 and end at the number of points")
+        hg = C.c_void_p()
+        check(_lib.load().qa_snn_build(self._h, int(off.shape[0] - 1), ptr(off), dim, ptr(X), int(k), float(prune),
+                                       int(max_degree) if max_degree else 0, C.byref(hg)))
+        return DeviceGraph(self, hg, int(off.shape[0] - 1))
+
+    # -- recursion driver on the device (csrc/recursion.cuh) --------------------------------------
+    def split_graph(self, graph, part, num_parts: int) -> "DeviceGraph":
+        """``G.subgraph(part)`` for every part of a node partition at once (``qa_graph_split``): ``part[v]`` in [0, num_parts) or -1.
+        ``graph`` is a host tuple ``(n, eu, ev, w)`` or ``DeviceGraph.device_graph(p)``."""
+        n, m, eu, ev, w = self._graph_args(graph)
+        part = np.ascontiguousarray(part, dtype=np.int32)
+        if part.shape[0] != n:
+            raise ValueError("part must have one entry per node")
+        hg = C.c_void_p()
+        check(_lib.load().qa_graph_split(self._h, n, m, ptr(eu), ptr(ev), ptr(w), ptr(part), int(num_parts), C.byref(hg)))
+        return DeviceGraph(self, hg, int(num_parts))
+
+    def concat_models(self, models) -> "IsingModel":
+        """Single-problem resident models -> one batched model (``qa_model_concat``); the inputs stay valid."""
+        arr = (C.c_void_p * len(models))(*[m._h for m in models])
+        hm = C.c_void_p()
+        check(_lib.load().qa_model_concat(self._h, len(models), arr, C.byref(hm)))
+        out = IsingModel._from_handle(self, hm)
+        out.sizes = [m.num_variables for m in models]
+        return out
+
+    def sample_model_batch(self, model: "IsingModel", reads_per_problem: int, states, beta_schedules, sweeps_per_beta: int, seeds,
+                           energies=None):
+        """Anneal every problem of a batched resident model in one launch.  ``beta_schedules``: [num_betas] shared, or
+        [num_problems][num_betas] -- one schedule per problem."""
+        beta_schedules = np.ascontiguousarray(beta_schedules, dtype=np.float64)
+        per_problem = beta_schedules.ndim == 2
+        num_betas = int(beta_schedules.shape[-1])
+        seeds = _as(seeds, np.uint64, "seeds")
+        P = len(model.sizes)
+        if per_problem and beta_schedules.shape[0] != P:
+            raise ValueError("one beta schedule per problem expected")
+        if not _is_tensor(states) and (states.dtype != np.int8 or not states.flags.c_contiguous):
+            raise ValueError("states must be a C-contiguous int8 array (it is updated in place)")
+        if energies is None:
+            energies = np.empty(P * int(reads_per_problem), dtype=np.float64)
+        st = QAStats()
+        done = check(_lib.load().qa_sa_sample_model_batch(self._h, model._h, int(reads_per_problem), ptr(states), ptr(energies), num_betas,
+                                                          ptr(beta_schedules), 1 if per_problem else 0, int(sweeps_per_beta), ptr(seeds),
+                                                          C.byref(st)))
+        return energies, st, done
+
     # -- model construction on the device (qa_build_*): graph = (n, eu, ev, w) in G.edges order ---
     def _graph_args(self, graph):
         n, eu, ev, w = graph
+        if isinstance(eu, int):            # raw device addresses (DeviceGraph.device_graph): (n, eu, ev, w, m)
+            return int(n), int(graph[4]), eu, ev, w
         if not _is_tensor(eu):
             eu = np.ascontiguousarray(eu, dtype=np.int32)
             ev = np.ascontiguousarray(ev, dtype=np.int32)
@@ -256,6 +316,51 @@ class Context:
         return energies, st, done
 
 
+class DeviceGraph:
+    """Edge lists that live on the GPU (``qa_graph``), one per point set; ``graph(p)`` copies one out as the host tuple
+    ``(n, eu, ev, w)`` of snn.py, ``device_graph(p)`` names it by device addresses for ``Context.build_*``."""
+
+    def __init__(self, ctx: Context, handle, num_problems: int):
+        self.ctx = ctx
+        self._h = handle
+        self.num_problems = num_problems
+
+    def num_nodes(self, problem: int = 0) -> int:
+        return check(_lib.load().qa_graph_num_nodes(self._h, int(problem)))
+
+    def num_edges(self, problem: int = -1) -> int:
+        return int(check(_lib.load().qa_graph_num_edges(self._h, int(problem))))
+
+    def graph(self, problem: int = 0):
+        m = self.num_edges(problem)
+        eu, ev, w = np.empty(m, dtype=np.int32), np.empty(m, dtype=np.int32), np.empty(m, dtype=np.float64)
+        check(_lib.load().qa_graph_get_edges(self._h, int(problem), ptr(eu), ptr(ev), ptr(w)))
+        return self.num_nodes(problem), eu.astype(np.int64), ev.astype(np.int64), w
+
+    def nodes(self, problem: int = 0) -> np.ndarray:
+        """Parent node index of every node of child ``problem`` (graphs made by ``Context.split_graph``)."""
+        n = self.num_nodes(problem)
+        out = np.empty(n, dtype=np.int32)
+        check(_lib.load().qa_graph_get_nodes(self._h, int(problem), ptr(out)))
+        return out
+
+    def device_graph(self, problem: int = 0):
+        eu, ev, w = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(_lib.load().qa_graph_device_edges(self._h, int(problem), C.byref(eu), C.byref(ev), C.byref(w)))
+        return self.num_nodes(problem), int(eu.value or 0), int(ev.value or 0), int(w.value or 0), self.num_edges(problem)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().qa_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class IsingModel:
     """A model resident on the GPU (``qa_model``): CSR adjacency in neal's push_back order + h."""
 
@@ -293,6 +398,11 @@ class IsingModel:
             raise ValueError("grp/coef must have one entry per variable")
         check(_lib.load().qa_model_set_groups(self._h, int(lam.shape[0]), ptr(grp), ptr(coef), ptr(lam), ptr(kappa)))
         self.num_groups = int(lam.shape[0])
+
+    def enable_dense(self, cases_per_cell: int = 1) -> bool:
+        """Derive the dense k-way form (W, P) on the device; True when the model has it: ``mode=QA_MODE_THROUGHPUT`` then runs the
+        fp64 tensor-core kernel (``qa_model_enable_dense``)."""
+        return bool(check(_lib.load().qa_model_enable_dense(self._h, int(cases_per_cell))))
 
     @property
     def max_degree(self) -> int:

@@ -102,6 +102,27 @@ def graph_arrays(G) -> Tuple[List[Hashable], np.ndarray, np.ndarray, np.ndarray]
         nodes, eu, ev, w = G
         labels = list(range(nodes)) if isinstance(nodes, (int, np.integer)) else list(nodes)
         return labels, np.asarray(eu, dtype=np.int64), np.asarray(ev, dtype=np.int64), np.asarray(w, dtype=np.float64)
+    root = getattr(G, "_graph", None)
+    if root is not None:
+        # A subgraph VIEW (the recursion of BQM_clustering.py:113-203 calls itself on G.subgraph(S0 / S1)): networkx iterates
+        # the nodes and adjacencies of a view smaller than half its parent in SET order, i.e. in an order that depends on
+        # PYTHONHASHSEED -- the reference inherits that nondeterminism.  Pinned here to the induced subgraph in the ROOT
+        # graph's node and adjacency order (what a view of more than half the parent yields, and what qa_graph_split emits).
+        while getattr(root, "_graph", None) is not None:
+            root = root._graph
+        members = set(G.nodes)
+        labels = [v for v in root.nodes if v in members]
+        pos = {v: i for i, v in enumerate(labels)}
+        eu_l, ev_l, w_l = [], [], []
+        seen = set()
+        for u in labels:
+            for v, d in root.adj[u].items():
+                if v in members and v not in seen:
+                    eu_l.append(pos[u])
+                    ev_l.append(pos[v])
+                    w_l.append(d["weight"])
+            seen.add(u)
+        return labels, np.asarray(eu_l, dtype=np.int64), np.asarray(ev_l, dtype=np.int64), np.asarray(w_l, dtype=np.float64)
     labels = list(G.nodes)
     pos = {v: i for i, v in enumerate(labels)}
     m = G.number_of_edges()
@@ -129,8 +150,9 @@ def _canonical(r: np.ndarray, c: np.ndarray, q: np.ndarray):
 def _total_weight(G, n: int, eu: np.ndarray, ev: np.ndarray, w: np.ndarray) -> float:
     """``G.size(weight='weight')`` exactly as networkx computes it: sum of the weighted degrees (node order, each degree
     summed in adjacency order) divided by 2 -- NOT the plain sum of edge weights (differs in the last bits)."""
-    if not isinstance(G, tuple):
-        return float(G.size(weight="weight"))
+    if not isinstance(G, tuple) and getattr(G, "_graph", None) is None:
+        return float(G.size(weight="weight"))      # (Python >= 3.12: sum() is compensated; bit-pinned by the golden fixtures)
+    # arrays and subgraph views: plain left-to-right adds in the canonical order (graph_arrays), like the device builders
     deg = _edge_order_sum(n, eu, ev, np.asarray(w, dtype=np.float64))  # adjacency order of a graph built edge by edge
     return _seq_sum(deg) / 2
 
@@ -281,6 +303,38 @@ def dqm_model(G, num_of_clusters: int, gamma: float, penalty: Optional[float] = 
     r, c, q = _canonical(np.concatenate([er, oh_r]), np.concatenate([ec, oh_c]), np.concatenate([eq, oh_q]))
     h, J, off = qubo_to_ising_vectors(lin_x, r, c, q)
     return LoweredModel(h, r, c, J, off + offset_onehot, var_labels, None, meta)
+
+
+def dense_kway_model(A: np.ndarray, num_of_clusters: int, gamma: float, penalty: Optional[float] = None,
+                     labels: Optional[List[Hashable]] = None) -> LoweredModel:
+    """BASELINE.json config 5: the DQM-style k-way model of ``clustering_dqm`` (DQM_clustering.py:29-43, "intended" semantics)
+    on a DENSE symmetric affinity ``A`` (zero diagonal) instead of a sparse SNN graph: every pair of cells is an edge, so
+    same-case quadratic = 2*gamma - 2*A_ij for all i != j, linear_i = gamma*(1 - n/K) + sum_j A_ij, one-hot penalty as in
+    ``dqm_model``.  Built without a networkx round trip (n^2 K / 2 couplers, emitted directly in dimod's vector order:
+    row = larger index, ascending columns).  ``meta['num_cases']`` lets the sampler enable the tensor-core form."""
+    A = np.asarray(A, dtype=np.float64)
+    n, K = A.shape[0], int(num_of_clusters)
+    if A.shape != (n, n):
+        raise ValueError("A must be square")
+    labels = list(range(n)) if labels is None else list(labels)
+    lin = gamma * (1 - n / K) + A.sum(axis=1)
+    pair_q = 2 * gamma - 2 * A                       # QUBO coefficient of x_ic x_jc
+    Apen = float(np.abs(lin).max() + np.abs(pair_q).sum(axis=1).max() + 1.0) if penalty is None else float(penalty)
+    meta = {"kind": "dqm", "builder": "dense_kway", "num_cases": K, "cells": labels, "penalty": Apen, "gamma": gamma,
+            "semantics": "intended", "dense": True}
+    # row v = i*K + c holds, ascending: (j*K + c) for j < i, then (i*K + c2) for c2 < c
+    cnt = (np.arange(n)[:, None] + np.arange(K)[None, :]).ravel()             # couplers per row
+    rows = np.repeat(np.arange(n * K, dtype=np.int64), cnt)
+    first = np.cumsum(cnt) - cnt
+    pos = np.arange(rows.shape[0], dtype=np.int64) - first[rows]             # position inside the row
+    i, c = rows // K, rows % K
+    inter = pos < i
+    cols = np.where(inter, pos * K + c, i * K + (pos - i))
+    q = np.where(inter, pair_q[i, np.minimum(pos, n - 1)], 2.0 * Apen)
+    lin_x = np.repeat(lin, K) - Apen
+    h, J, off = qubo_to_ising_vectors(lin_x, rows.astype(np.int32), cols.astype(np.int32), q)
+    var_labels = [(v, cc) for v in labels for cc in range(K)]
+    return LoweredModel(h, rows.astype(np.int32), cols.astype(np.int32), J, off + Apen * n, var_labels, None, meta)
 
 
 def slack_coefficients(upper: int) -> List[int]:

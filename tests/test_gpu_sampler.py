@@ -204,28 +204,25 @@ def torch_cuda():
 
 
 def test_level_batched_recursive_bipartition(built):
-    """All sub-graphs of a recursion level are annealed in one batched launch; every level's best energies equal the oracle's
-    on the same inputs, and four well-separated blobs are recovered as the four leaves."""
+    """All sub-graphs of a recursion level are extracted, built and annealed on the device in one batched launch; level 0's best
+    energy equals the oracle's on the same inputs, and four well-separated blobs are recovered as the four leaves."""
     from scrna_seq_qannealing_clustering_b200 import clustering
     from scrna_seq_qannealing_clustering_b200.engine import Context
     X, truth = snn.gaussian_mixture_embedding(240, dim=8, centres=4, sep=9.0, seed=1)
     G = snn.to_networkx(snn.snn_graph(X, k=10))
     with Context(0) as ctx:
-        labels, levels, energies = clustering.recursive_bipartition_batched(G, gamma_factor=0.05, k=8.0, size_limit=30, iter_limit=1,
+        labels, levels, energies = clustering.recursive_bipartition_batched(G, gamma_factor=0.05, k=8.0, size_limit=30, iter_limit=2,
                                                                             num_reads=96, num_sweeps=300, seed=3, context=ctx)
-    assert len(levels) == 2 and len(levels[0]) == 1 and len(levels[1]) == 2      # one launch per level
-    assert set(labels) == set(G.nodes)
-    # leaves are pure w.r.t. the planted blobs (a leaf may hold one or two whole blobs, never a split one)
+    assert [len(lv) for lv in levels] == [1, 2, 4]      # one launch per level
+    assert set(labels) == set(G.nodes) and len(set(labels.values())) == 4
     node_truth = {str(i): int(t) for i, t in enumerate(truth)}
     for leaf in set(labels.values()):
-        members = [n for n, l in labels.items() if l == leaf]
-        blobs = {node_truth[n] for n in members}
-        for b in blobs:
-            assert sum(node_truth[n] == b for n in members) == sum(t == b for t in node_truth.values())
-    # level 0 reproduced with the oracle: same model, same seeds, same initial states -> same best energy
-    m = models.cut_balance_model(G, 0.05, k=8.0, structured=False)
-    br = schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights)
+        assert len({node_truth[n] for n, l in labels.items() if l == leaf}) == 1      # every leaf is one planted blob
+    # level 0 reproduced with the oracle: same structured model, same seeds, same initial states -> same best energy
+    lab, eu, ev, w = models.graph_arrays(G)     # as arrays: plain left-to-right sums like the device builder (G.size() compensates)
+    m = models.cut_balance_model((lab, eu, ev, w), 0.05, k=8.0, structured=True)
+    br = schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights, None)
     betas, spb = schedule.make_beta_schedule(br, 300, 1, "geometric")
     st = schedule.random_spin_states(96, m.num_variables, 3)
-    e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, st, betas, spb, schedule.per_read_seeds(3, 96))
+    e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, st, betas, spb, schedule.per_read_seeds(3, 96), groups=m.groups.astuple())
     assert energies[0][0] == float(e.min() + m.offset)

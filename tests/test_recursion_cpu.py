@@ -1,28 +1,79 @@
-"""Host logic of the level-batched recursion (clustering.recursive_bipartition_batched) on CPU: the batched launch is
-replaced by an oracle-backed stand-in with the same signature, so the level bookkeeping, the per-problem seeds / initial
-states and the split rule are checked without a GPU (the GPU test runs the same driver through the C ABI)."""
+"""Host logic of the level-batched recursion (clustering.recursive_bipartition_batched) on CPU: the device entry points it
+drives (qa_graph_split, qa_build_cut_balance, qa_model_concat, qa_sa_sample_model_batch) are replaced by numpy / oracle-backed
+stand-ins with the same semantics, so the level bookkeeping, the per-problem seeds / initial states / beta schedules and the
+termination rules are checked without a GPU (tests/test_gpu_recursion.py runs the same driver through the C ABI)."""
+import networkx as nx
 import numpy as np
+import pytest
 
 from oracle import oracle
 from scrna_seq_qannealing_clustering_b200 import clustering, models, schedule, snn
 
 
+def host_split(graph, part_of, P):
+    """Restatement of qa_graph_split: children keep the parent's node order and edge order, nodes relabelled by rank."""
+    n, eu, ev, w = graph
+    out = []
+    for p in range(P):
+        nodes = np.flatnonzero(part_of == p)
+        local = np.full(n, -1, dtype=np.int64)
+        local[nodes] = np.arange(len(nodes))
+        keep = (part_of[eu] == p) & (part_of[ev] == p)
+        out.append((len(nodes), local[eu[keep]], local[ev[keep]], np.asarray(w)[keep]))
+    return out
+
+
+class _Split:
+    def __init__(self, graphs):
+        self.graphs = graphs
+
+    def device_graph(self, p):
+        return self.graphs[p]
+
+    graph = device_graph
+
+    def close(self):
+        pass
+
+
+class _Model:
+    def __init__(self, m):
+        self.m = m
+        self.num_variables = m.num_variables
+
+    def get_ising(self):
+        return self.m.h, self.m.starts, self.m.ends, self.m.weights
+
+    def close(self):
+        pass
+
+
 class OracleBatchContext:
-    """`Context.sample_ising_batch` semantics: independent problems, `reads_per_problem` reads each, states updated in place."""
+    """Stand-in for the `Context` methods the driver uses; every batched launch is counted."""
 
     def __init__(self):
         self.calls = 0
 
-    def sample_ising_batch(self, voff, coff, h, starts, ends, w, rpp, states, betas, spb, seeds):
+    def split_graph(self, graph, part_of, P):
+        return _Split(host_split(graph, np.asarray(part_of), P))
+
+    def build_cut_balance(self, graph, gamma_factor, k):
+        m = models.cut_balance_model(graph, gamma_factor, k=k, structured=True)
+        return _Model(m), m.offset, m.meta["gamma"]
+
+    def concat_models(self, gms):
+        return type("Batch", (), {"parts": list(gms), "close": lambda self: None})()
+
+    def sample_model_batch(self, bm, rpp, states, betas, spb, seeds):
         self.calls += 1
-        P = len(voff) - 1
-        e = np.empty(P * rpp)
+        e = np.empty(len(bm.parts) * rpp)
         off = 0
-        for p in range(P):
-            n = int(voff[p + 1] - voff[p])
-            sl = slice(int(coff[p]), int(coff[p + 1]))
+        for p, gm in enumerate(bm.parts):
+            m, n = gm.m, gm.num_variables
             st = states[off:off + rpp * n].reshape(rpp, n).copy()
-            ee, _ = oracle.sample_ising(h[voff[p]:voff[p + 1]], starts[sl], ends[sl], w[sl], st, betas, spb, seeds[p * rpp:(p + 1) * rpp])
+            b = betas[p] if np.ndim(betas) == 2 else betas
+            ee, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, st, np.ascontiguousarray(b), spb, seeds[p * rpp:(p + 1) * rpp],
+                                        groups=m.groups.astuple() if m.groups is not None else None)
             states[off:off + rpp * n] = st.ravel()
             e[p * rpp:(p + 1) * rpp] = ee
             off += rpp * n
@@ -33,19 +84,23 @@ def test_four_blobs_are_recovered_with_one_launch_per_level():
     X, truth = snn.gaussian_mixture_embedding(240, dim=8, centres=4, sep=9.0, seed=1)
     G = snn.to_networkx(snn.snn_graph(X, k=10))
     ctx = OracleBatchContext()
-    labels, levels, energies = clustering.recursive_bipartition_batched(G, gamma_factor=0.05, k=8.0, size_limit=30, iter_limit=1,
+    labels, levels, energies = clustering.recursive_bipartition_batched(G, gamma_factor=0.05, k=8.0, size_limit=30, iter_limit=2,
                                                                         num_reads=96, num_sweeps=300, seed=3, context=ctx)
-    assert ctx.calls == 2 and [len(lv) for lv in levels] == [1, 2]
+    # min_size rule, literally: a level that stops writes nothing, so the blobs (halves <= size_limit) are the leaves
+    assert ctx.calls == 3 and [len(lv) for lv in levels] == [1, 2, 4]
     assert set(labels) == set(G.nodes) and len(set(labels.values())) == 4
     node_truth = {str(i): int(t) for i, t in enumerate(truth)}
     for leaf in set(labels.values()):
         assert len({node_truth[n] for n, l in labels.items() if l == leaf}) == 1      # every leaf is one planted blob
-    # level 0 is exactly one neal-style call on the whole graph with the documented seeds / initial states
-    m = models.cut_balance_model(G, 0.05, k=8.0, structured=False)
-    br = schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights)
+    # level 0 is exactly one neal-style call on the whole graph with the documented seeds / initial states / default range
+    # (graph given as arrays: networkx's G.size() sums with Python 3.12's compensated sum(), the device builders and the array
+    # path of models.py with plain left-to-right adds -- one ulp apart in gamma)
+    lab, eu, ev, w = models.graph_arrays(G)
+    m = models.cut_balance_model((lab, eu, ev, w), 0.05, k=8.0, structured=True)
+    br = schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights, None)
     betas, spb = schedule.make_beta_schedule(br, 300, 1, "geometric")
     st = schedule.random_spin_states(96, m.num_variables, 3)
-    e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, st, betas, spb, schedule.per_read_seeds(3, 96))
+    e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, st, betas, spb, schedule.per_read_seeds(3, 96), groups=m.groups.astuple())
     assert energies[0][0] == float(e.min() + m.offset)
 
 
@@ -55,11 +110,70 @@ def test_size_limit_and_iteration_limit_stop_the_recursion():
     ctx = OracleBatchContext()
     labels, levels, _ = clustering.recursive_bipartition_batched(G, 0.05, size_limit=1000, iter_limit=5, num_reads=32, num_sweeps=100,
                                                                  seed=1, context=ctx)
-    assert ctx.calls == 1 and len(set(labels.values())) <= 2            # halves are below size_limit: no second level
+    assert ctx.calls == 1 and len(set(labels.values())) == 1            # min_size writes nothing when it stops: one cluster
     ctx = OracleBatchContext()
     labels, levels, _ = clustering.recursive_bipartition_batched(G, 0.05, size_limit=5, iter_limit=0, num_reads=32, num_sweeps=100,
                                                                  seed=1, context=ctx)
     assert ctx.calls == 1                                               # iteration limit reached at the first level
+    ctx = OracleBatchContext()
+    labels, levels, _ = clustering.recursive_bipartition_batched(G, 0.05, terminate_on="once", num_reads=32, num_sweeps=100, seed=1,
+                                                                 context=ctx)
+    assert ctx.calls == 1 and len(set(labels.values())) == 2            # `once`: one split, both halves labelled
+
+
+class _RecordingSampler:
+    """Records (node set, S0, S1) of every sampler call of the call-by-call recursion; anneals with the oracle."""
+
+    def __init__(self):
+        self.calls = []
+
+    def sample(self, model, num_reads=None, num_sweeps=None, seed=None, sorted=False, **kw):
+        from scrna_seq_qannealing_clustering_b200.sampleset import SampleSet
+        br = schedule.default_ising_beta_range(model.h, model.starts, model.ends, model.weights, None)
+        betas, spb = schedule.make_beta_schedule(br, num_sweeps, 1, "geometric")
+        st = schedule.random_spin_states(num_reads, model.num_variables, seed)
+        e, _ = oracle.sample_ising(model.h, model.starts, model.ends, model.weights, st, betas, spb,
+                                   schedule.per_read_seeds(seed, num_reads), groups=model.groups.astuple())
+        ss = SampleSet.from_samples((((st + 1) // 2).astype(np.int8), model.labels), energy=e + model.offset, vartype="BINARY").sorted()
+        first = ss.first.sample
+        self.calls.append((frozenset(model.labels), frozenset(v for v in model.labels if not first[v])))
+        return ss
+
+
+@pytest.mark.parametrize("rule,kw", [("min_size", {"size_limit": 30, "iter_limit": 3}), ("conf", {"iter_limit": 2}),
+                                     ("iter_limit", {"iter_limit": 2}), ("once", {})])
+def test_batched_driver_builds_the_tree_of_the_call_by_call_recursion(rule, kw):
+    """Every termination rule: the level-batched driver anneals exactly the sub-graphs the reference-shaped recursion
+    (clustering_bqm calling itself on G.subgraph(S0 / S1)) anneals, and splits them identically."""
+    X, _ = snn.gaussian_mixture_embedding(200, dim=8, centres=4, sep=9.0, seed=4)
+    G = snn.to_networkx(snn.snn_graph(X, k=10))
+    rec = _RecordingSampler()
+    clustering.clustering_bqm(G.copy(), 0, {"name": "t"}, "rec", 0.05, terminate_on=rule, sampler=rec, device_build=False,
+                              num_reads=24, num_sweeps=60, seed=9, **kw)
+    ctx = OracleBatchContext()
+    _, levels, _ = clustering.recursive_bipartition_batched(G, 0.05, terminate_on=rule, num_reads=24, num_sweeps=60, seed=9, context=ctx,
+                                                            **kw)
+    assert {c[0] for c in rec.calls} == {frozenset(part) for lv in levels for part in lv}
+    assert ctx.calls == len(levels)
+
+
+def test_split_keeps_the_order_networkx_subgraphs_have():
+    """qa_graph_split's contract (restated by host_split): a child's edge list equals graph_arrays(G.subgraph(part))."""
+    gz = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "graphs.npz")
+    for name in ("blobs", "noisy_moons"):
+        labels = [str(x) for x in gz[f"{name}_labels"]]
+        G = nx.Graph()
+        G.add_nodes_from(labels)
+        for u, v, w in zip(gz[f"{name}_eu"], gz[f"{name}_ev"], gz[f"{name}_w"]):
+            G.add_edge(labels[u], labels[v], weight=float(w))
+        lab, eu, ev, w = models.graph_arrays(G)
+        rng = np.random.default_rng(3)
+        part_of = rng.integers(-1, 3, size=len(lab)).astype(np.int32)
+        for p, child in enumerate(host_split((len(lab), eu, ev, w), part_of, 3)):
+            sub = G.subgraph([lab[i] for i in np.flatnonzero(part_of == p)])
+            sl, su, sv, sw = models.graph_arrays(sub)
+            assert sl == [lab[i] for i in np.flatnonzero(part_of == p)]
+            assert np.array_equal(su, child[1]) and np.array_equal(sv, child[2]) and np.array_equal(sw, child[3])
 
 
 # ---- the reference's termination rules, restated literally (ADVICE r1: the default `conf` path must match) ----------
