@@ -23,6 +23,13 @@
  *    pointers of the context's device (detected with cudaPointerGetAttributes); model
  *    and scratch memory is owned by the library, every other buffer by the caller.
  *  - calls block until their results are complete.  A qa_ctx is not re-entrant.
+ *  - STREAMS: a context launches on its own non-blocking CUDA stream and synchronises it before a call returns, so results
+ *    are complete on return for any consumer.  The library does NOT order itself against the caller's streams: a device
+ *    buffer handed in (states, seeds, schedules, graph arrays) must be complete -- synchronise the producing stream, or
+ *    record an event and wait for it, before the call (bench.py: torch.cuda.synchronize()).
+ *  - duplicate couplers (the same pair listed twice) are legal, as for neal; the warp-per-read kernel then issues two
+ *    reductions to one address from one instruction, whose relative order the PTX memory model does not define (observed:
+ *    lane order).  Vectors derived from a BQM never contain duplicates.
  *  - spins are int8 +1/-1, states are row-major [num_reads][n] and are IN/OUT (initial
  *    states in, final states out), exactly like neal's `states` argument.
  */

@@ -52,34 +52,45 @@ __host__ __device__ inline size_t dn_smem_bytes(int warps) {
     return (size_t)warps * 8 * DnGeom<K>::LD * sizeof(double);
 }
 
-// inter-cell fields of the 8 cells i0..i0+7 for all columns of the warp: C[t][e] (fragment layout above)
+// inter-cell fields of the 8 cells i0..i0+7 for all columns of the warp: C[t][e] (fragment layout above).
+// The loads of group g + 1 (8 doubles of W, 4K spin words) are issued before the 128 MMAs of group g: a warp alone on its
+// scheduler keeps the fp64 tensor pipe fed.
 template <int K>
 __device__ __forceinline__ void dn_block_fields(const DenseDesc &Dd, const uint32_t *__restrict__ SW, int i0, int lane,
                                                 double (&C)[4 * K][2]) {
     constexpr int NT = DnGeom<K>::NT, COLS = DnGeom<K>::COLS;
     const int r8 = lane >> 2, kap = lane & 3;
-    const double *wrow = Dd.W + (size_t)(i0 + r8) * Dd.ncp + kap * 8;
-    const uint32_t *sw = SW + r8 * NT;
+    const double2 *ap = reinterpret_cast<const double2 *>(Dd.W + (size_t)(i0 + r8) * Dd.ncp + kap * 8);
+    const uint4 *wp = reinterpret_cast<const uint4 *>(SW + r8 * NT);
 #pragma unroll
     for (int t = 0; t < NT; ++t) C[t][0] = C[t][1] = 0.0;
-    for (int g = 0; g < Dd.ngrp; ++g) {
+    double2 an[4];
+    uint4 wn[K];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) an[q] = __ldg(ap + q);
+#pragma unroll
+    for (int q = 0; q < K; ++q) wn[q] = __ldcg(wp + q);
+    const int ngrp = Dd.ngrp;
+    for (int g = 0; g < ngrp; ++g) {
         double a[8];
-        const double2 *ap = reinterpret_cast<const double2 *>(wrow + g * 32);
+        uint32_t w[NT];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const double2 v = __ldg(ap + q);
-            a[2 * q] = v.x;
-            a[2 * q + 1] = v.y;
+            a[2 * q] = an[q].x;
+            a[2 * q + 1] = an[q].y;
         }
-        uint32_t w[NT];
-        const uint4 *wp = reinterpret_cast<const uint4 *>(sw + (size_t)g * COLS);
 #pragma unroll
         for (int q = 0; q < K; ++q) {
-            const uint4 v = __ldcg(wp + q);
-            w[4 * q] = v.x >> (kap * 8);
-            w[4 * q + 1] = v.y >> (kap * 8);
-            w[4 * q + 2] = v.z >> (kap * 8);
-            w[4 * q + 3] = v.w >> (kap * 8);
+            w[4 * q] = wn[q].x >> (kap * 8);
+            w[4 * q + 1] = wn[q].y >> (kap * 8);
+            w[4 * q + 2] = wn[q].z >> (kap * 8);
+            w[4 * q + 3] = wn[q].w >> (kap * 8);
+        }
+        if (g + 1 < ngrp) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) an[q] = __ldg(ap + (size_t)(g + 1) * 16 + q);
+#pragma unroll
+            for (int q = 0; q < K; ++q) wn[q] = __ldcg(wp + (size_t)(g + 1) * (COLS / 4) + q);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -167,6 +178,9 @@ __global__ void __launch_bounds__(128, 2) k_anneal_dense(AnnealParams P, DenseDe
                     for (int c = 0; c < K; ++c) wv[c] = __ldcg(myw + c);
                     const int b0 = i0 & 31;
                     bool dirty = false;
+                    // the block's own 8 x 8 couplings, two per lane: rows 0-3 in wlo, rows 4-7 in whi, column = lane & 7
+                    const double wlo = __ldg(Dd.W + (size_t)(i0 + (lane >> 3)) * Dd.ncp + i0 + (lane & 7));
+                    const double whi = __ldg(Dd.W + (size_t)(i0 + 4 + (lane >> 3)) * Dd.ncp + i0 + (lane & 7));
                     for (int m = 0; m < 8; ++m) {
                         const int i = i0 + m;
                         if (i >= ncells) break;
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(128, 2) k_anneal_dense(AnnealParams P, DenseDe
                             if (m < 7 && __any_sync(FULL_MASK, acc)) {
                                 const double d2 = acc ? (s[c] > 0 ? 2.0 : -2.0) : 0.0;   // 2 * s_new
                                 for (int m2 = m + 1; m2 < 8; ++m2) {
-                                    const double wj = __ldg(Dd.W + (size_t)(i0 + m2) * Dd.ncp + i);
+                                    const double wj = __shfl_sync(FULL_MASK, m2 < 4 ? wlo : whi, (m2 & 3) * 8 + m);
                                     Fb[m2 * LD + lane * K + c] += d2 * wj;
                                 }
                             }

@@ -1890,8 +1890,8 @@ int run_anneal(qa_ctx *ctx, qa_model *M, int32_t reads_per_problem, int8_t *d_st
         QA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&bps, fn, warps * 32, smem, cudaOccupancyDefault));
         if (bps < 1) return fail(QA_ERR_CUDA, "dense kernel does not fit on an SM");
         const int64_t total_tiles = (reads_per_problem + 31) / 32;
-        // few tiles: one warp per CTA on as many SMs as there are tiles (idle warps leave at once)
-        const int64_t grid = std::min<int64_t>((int64_t)bps * ctx->num_sms, total_tiles);
+        // every warp pulls 32-read tiles from a counter; no more CTAs than the tiles can fill (warps without a tile leave at once)
+        const int64_t grid = std::min<int64_t>((int64_t)bps * ctx->num_sms, (total_tiles + warps - 1) / warps);
         const int64_t stride = (int64_t)M->dn.ngrp * 32 * K;
         rc = ensure(ctx->sf, (size_t)grid * warps * stride * sizeof(uint32_t));
         if (rc) return rc;

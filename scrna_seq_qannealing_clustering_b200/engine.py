@@ -27,6 +27,19 @@ def _as(x, dtype, name):
     return a
 
 
+def _check_states(states):
+    """The library updates ``states`` in place through a raw pointer: a host array must already be C-contiguous int8 (a silent
+    conversion would anneal a temporary copy, a wrong dtype would corrupt memory); a device tensor must be int8 and contiguous."""
+    if _is_tensor(states):
+        dt = str(getattr(states, "dtype", "int8"))
+        if "int8" not in dt or "uint8" in dt:
+            raise ValueError("states must be an int8 tensor")
+        if hasattr(states, "is_contiguous") and not states.is_contiguous():
+            raise ValueError("states must be contiguous")
+    elif states.dtype != np.int8 or not states.flags.c_contiguous:
+        raise ValueError("states must be a C-contiguous int8 array (it is updated in place)")
+
+
 class DeviceBuffer:
     """A device allocation of the library (``qa_dev_alloc``) with a shape: lets the host layer keep a state matrix on the
     GPU from creation to the top-k export without depending on a tensor library.  Quacks like a tensor for ``_lib.ptr``."""
@@ -221,8 +234,7 @@ class Context:
         P = len(model.sizes)
         if per_problem and beta_schedules.shape[0] != P:
             raise ValueError("one beta schedule per problem expected")
-        if not _is_tensor(states) and (states.dtype != np.int8 or not states.flags.c_contiguous):
-            raise ValueError("states must be a C-contiguous int8 array (it is updated in place)")
+        _check_states(states)
         if energies is None:
             energies = np.empty(P * int(reads_per_problem), dtype=np.float64)
         st = QAStats()
@@ -233,9 +245,10 @@ class Context:
 
     # -- model construction on the device (qa_build_*): graph = (n, eu, ev, w) in G.edges order ---
     def _graph_args(self, graph):
+        if len(graph) == 5:                # raw device addresses (DeviceGraph.device_graph): (n, eu, ev, w, m)
+            n, eu, ev, w, m = graph
+            return int(n), int(m), int(eu), int(ev), int(w)
         n, eu, ev, w = graph
-        if isinstance(eu, int):            # raw device addresses (DeviceGraph.device_graph): (n, eu, ev, w, m)
-            return int(n), int(graph[4]), eu, ev, w
         if not _is_tensor(eu):
             eu = np.ascontiguousarray(eu, dtype=np.int32)
             ev = np.ascontiguousarray(ev, dtype=np.int32)
@@ -285,6 +298,7 @@ class Context:
         seeds = _as(seeds, np.uint64, "seeds")
         n = int(h.shape[0])
         m = int(starts.shape[0])
+        _check_states(states)
         num_reads = int(states.shape[0]) if n else 0
         if energies is None:
             energies = np.empty(num_reads, dtype=np.float64)
@@ -306,6 +320,7 @@ class Context:
         beta_schedule = _as(beta_schedule, np.float64, "beta_schedule")
         seeds = _as(seeds, np.uint64, "seeds")
         num_problems = int(var_offsets.shape[0]) - 1
+        _check_states(states)
         if energies is None:
             energies = np.empty(num_problems * int(reads_per_problem), dtype=np.float64)
         st = QAStats()
@@ -422,9 +437,7 @@ class IsingModel:
         beta_schedule = _as(beta_schedule, np.float64, "beta_schedule")
         seeds = _as(seeds, np.uint64, "seeds")
         num_reads = int(states.shape[0])
-        if not _is_tensor(states):
-            if states.dtype != np.int8 or not states.flags.c_contiguous:
-                raise ValueError("states must be a C-contiguous int8 array (it is updated in place)")
+        _check_states(states)
         if energies is None:
             energies = np.empty(num_reads, dtype=np.float64)
         cb = None

@@ -115,20 +115,24 @@ class _Recording(B200SimulatedAnnealingSampler):
         return ss
 
 
-@pytest.mark.parametrize("rule,kw", [("min_size", {"size_limit": 30, "iter_limit": 3}), ("conf", {"iter_limit": 2})])
-def test_batched_recursion_reproduces_clustering_bqm_on_graph_blobs(ctx, rule, kw):
+@pytest.mark.parametrize("rule,reads,kw,min_levels", [("min_size", 48, {"size_limit": 30, "iter_limit": 3}, 2),
+                                                      ("conf", 48, {"iter_limit": 2}, 1),      # ratio branch: e0 / e3 decides
+                                                      ("conf", 3, {"iter_limit": 2}, 3),       # <= 3 energies: size branch recurses
+                                                      ("iter_limit", 16, {"iter_limit": 2}, 3), ("once", 16, {}, 1)])
+def test_batched_recursion_reproduces_clustering_bqm_on_graph_blobs(ctx, rule, reads, kw, min_levels):
     """the level-batched device recursion anneals the same sub-graphs, finds the same halves and the same best
-    energies as `clustering_bqm` calling the sampler once per sub-graph (both build on the device, both use per-call seeding)."""
+    energies as `clustering_bqm` calling the sampler once per sub-graph (both build on the device, both use per-call seeding),
+    for every termination rule of the reference."""
     G = load_graph("blobs")
     rec = _Recording(context=ctx)
-    clustering.clustering_bqm(G.copy(), 0, {"name": "blobs"}, "b200", 0.05, terminate_on=rule, sampler=rec, num_reads=48,
+    clustering.clustering_bqm(G.copy(), 0, {"name": "blobs"}, "b200", 0.05, terminate_on=rule, sampler=rec, num_reads=reads,
                               num_sweeps=120, seed=21, **kw)
-    labels, levels, energies = clustering.recursive_bipartition_batched(G, 0.05, terminate_on=rule, num_reads=48, num_sweeps=120,
+    labels, levels, energies = clustering.recursive_bipartition_batched(G, 0.05, terminate_on=rule, num_reads=reads, num_sweeps=120,
                                                                         seed=21, context=ctx, write_labels=True, **kw)
     want = {c[0]: c for c in rec.calls}
     got = {frozenset(part): e for lv, es in zip(levels, energies) for part, e in zip(lv, es)}
     assert set(want) == set(got)
     for nodes, e in got.items():
         assert e == want[nodes][2]                      # best energy of every sub-graph, bit for bit
-    assert len(levels) >= 2 and set(labels) == set(G.nodes)
-    assert all("label0" in G.nodes[v] for v in G.nodes)
+    assert len(levels) >= min_levels and set(labels) == set(G.nodes)
+    assert all("label0" in G.nodes[v] for v in G.nodes) or rule in ("min_size", "iter_limit")

@@ -31,7 +31,8 @@ with Context(0) as ctx:
     t1 = time.time()
     ok = gm.enable_dense(a.K)
     print("dense form:", ok, f"{time.time() - t1:.3f} s", flush=True)
-    for reads, sweeps, mode in ((a.reads, a.sweeps, _lib.QA_MODE_THROUGHPUT), (a.reads, a.sweeps, _lib.QA_MODE_THROUGHPUT),
+    cold = 1000.0 * hot       # (the default cold end comes from the smallest non-zero coupling: ~1e7 on a Gaussian affinity)
+    for reads, sweeps, mode in ((a.reads, a.sweeps, _lib.QA_MODE_THROUGHPUT), (2 * a.reads, a.sweeps, _lib.QA_MODE_THROUGHPUT),
                                 (a.ref_reads, a.ref_sweeps, _lib.QA_MODE_REFERENCE)):
         if reads <= 0:
             continue
