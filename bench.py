@@ -13,6 +13,8 @@ per-rank best gather at N > 1).  Reads shard over ranks with no data-path collec
     cpu_baseline  the CPU oracle (restatement of neal's loop, oracle/) on a bounded sample of the same workload
     full_job / strong  the config AS STATED: 100 000 reads x 1000 sweeps, split over the N ranks (strong scaling), once;
            with the feasibility fraction of the reads and the time to the CPU arm's best energy
+    config5  BASELINE config 5 (dense Gaussian-affinity 4-way model, 4096 cells x 4) on the fp64 tensor-core kernel, with its own
+           roofline block (achieved TFLOP/s against the measured DMMA peak)
 
 ``--impl reference`` times the oracle alone, with all host threads, on bounded samples of the same workload.
 """
@@ -55,6 +57,9 @@ def parse_args():
     ap.add_argument("--no-full-job", action="store_true", help="skip the 100 000 reads x 1000 sweeps job (full_job / strong blocks)")
     ap.add_argument("--job-reads", type=int, default=100000, help="reads of the stated job (split over the ranks)")
     ap.add_argument("--job-sweeps", type=int, default=1000)
+    ap.add_argument("--no-config5", action="store_true", help="skip the dense tensor-core block (BASELINE config 5)")
+    ap.add_argument("--c5-reads", type=int, default=37888, help="reads per GPU of the config-5 block (148 SMs x 8 warps x 32 reads)")
+    ap.add_argument("--c5-sweeps", type=int, default=20)
     ap.add_argument("--budget-s", type=float, default=840.0,
                     help="wall-clock budget of the whole run: the stated job is shortened (fewer sweeps, said so) when it would not fit")
     return ap.parse_args()
@@ -131,7 +136,7 @@ class ClockSampler:
 
 
 KERNEL_NAMES = {1: "k_anneal_ref<groups> (one warp per read)", 2: "k_anneal_lockstep<push,groups> (32 reads per warp, eager updates)",
-                3: "k_anneal_lockstep<pull,groups> (throughput mode)",
+                5: "k_anneal_dense<K> (dense k-way model, fields by mma.sync f64)",
                 4: "k_anneal_replay<groups> (32 reads per warp, deferred exact updates, TMA-staged coupling slabs; auto-selected)"}
 
 
@@ -164,6 +169,73 @@ def run_cpu_sample(model, betas, spb, seed, reads, threads, states=None, seeds=N
                                 groups=model.groups.astuple() if model.groups is not None else None, nthreads=threads)
     dt = time.perf_counter() - t0
     return st["attempts"] / dt, dt, e + model.offset, states
+
+
+DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: tools/ubench_dmma.cu, profiles/r2_ubench_dmma_peak.log (DFMA: 24.7)
+
+
+def config5_block(args, ctx, dev, rank, world, allmax, cpu_threads):
+    """BASELINE.json config 5 (dense Gaussian-affinity QUBO, 4096 cells x 4 clusters, batched local fields on fp64 tensor cores):
+    `c5_reads` reads per GPU x `c5_sweeps` sweeps on k_anneal_dense (QA_MODE_THROUGHPUT), inputs resident.  Roofline: the kernel
+    is bound by the fp64 tensor pipe -- 2 * n_cells flops per attempt against the measured DMMA peak."""
+    import torch
+    from scrna_seq_qannealing_clustering_b200 import _lib, models, schedule, snn
+    from scrna_seq_qannealing_clustering_b200.engine import IsingModel
+    cells, K = 4096, 4
+    X, _ = snn.gaussian_mixture_embedding(cells, dim=15, centres=K, sep=4.0, seed=2)
+    m = models.dense_kway_model(snn.gaussian_affinity(X, k=10), K, 0.05)
+    n = m.num_variables
+    hot = schedule.default_ising_beta_range(m.h, m.starts, m.ends, m.weights, None)[0]
+    beta_range = (hot, 1000.0 * hot)     # the default cold end follows the smallest non-zero coupling: ~1e7 on a Gaussian affinity
+    betas, spb = schedule.make_beta_schedule(beta_range, args.c5_sweeps, 1, "geometric")
+    R = args.c5_reads
+    gm = IsingModel(ctx, m.h, m.starts, m.ends, m.weights)
+    try:
+        if not gm.enable_dense(K):
+            raise RuntimeError("config 5 model lost its dense k-way form")
+        g = torch.Generator(device=dev)
+        g.manual_seed(args.seed + 5 + rank)
+        states = torch.randint(0, 2, (R, n), dtype=torch.int8, device=dev, generator=g)
+        states.mul_(2).sub_(1)
+        head = states[:4].cpu().numpy() if cpu_threads else None
+        seeds = schedule.per_read_seeds(args.seed + 5, R, first_read=rank * R)
+        seeds_dev = torch.from_numpy(seeds.view(np.int64)).to(dev)
+        energies = torch.empty(R, dtype=torch.float64, device=dev)
+        betas_dev = torch.from_numpy(betas).to(dev)
+        torch.cuda.synchronize()
+        keep = states.clone()
+        gm.sample(states, betas_dev, spb, seeds_dev, mode=_lib.QA_MODE_THROUGHPUT, energies=energies)      # warm-up
+        states.copy_(keep)
+        torch.cuda.synchronize()
+        _, st, done = gm.sample(states, betas_dev, spb, seeds_dev, mode=_lib.QA_MODE_THROUGHPUT, energies=energies)
+        assert done == R and ctx.last_kernel == _lib.QA_KERNEL_DENSE
+        t = allmax(st.ms_anneal * 1e-3)
+        attempts = float(n) * len(betas) * spb * R * world
+        tflops = 2.0 * cells * attempts / t / 1e12
+        out = {"workload": f"config5: dense Gaussian-affinity {K}-way model, {cells} cells x {K} = {n} vars, {m.num_couplers} couplers",
+               "reads_per_gpu": R, "num_sweeps": len(betas) * spb, "beta_range": [float(beta_range[0]), float(beta_range[1])],
+               "mode": "QA_MODE_THROUGHPUT (neal's sweep order and RNG, fields by mma.sync f64; tolerance parity)",
+               "value": attempts / t, "unit": UNIT, "seconds": t, "acceptance": st.accepted / st.attempts,
+               "best_energy": float(energies.min().item() + m.offset),
+               "roofline": {"bound": "tensor", "achieved": tflops / world, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                            "frac": tflops / world / DMMA_PEAK_TFLOPS, "traffic": None, "kernel": "k_anneal_dense<4> (DMMA.8x8x4)",
+                            "flops_per_attempt": 2.0 * cells,
+                            "peak_source": "measured fp64 mma.sync m8n8k4 rate of this pool's B200 (profiles/r2_ubench_dmma_peak.log); "
+                                           "MEASURED_PEAKS.json carries no fp64 figure"}}
+        if cpu_threads:
+            # the CPU arm anneals the first reads: same trajectories (generic real weights), energies to 1e-9 of neal's order
+            hs = head.copy()
+            t0 = time.perf_counter()
+            from oracle import oracle
+            ce, cst = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, hs, betas, spb, seeds[:4], nthreads=cpu_threads)
+            dt = time.perf_counter() - t0
+            ge = energies[:4].cpu().numpy()
+            out["cpu_arm"] = {"reads": 4, "seconds": dt, "value": cst["attempts"] / dt, "cores": min(cpu_threads, 4),
+                              "final_states_identical_to_gpu": bool(np.array_equal(hs, states[:4].cpu().numpy())),
+                              "max_rel_energy_diff": float(np.max(np.abs(ge - ce) / np.maximum(np.abs(ce), 1.0)))}
+        return out
+    finally:
+        gm.close()
 
 
 def peaks():
@@ -297,9 +369,7 @@ def main():
         e, st, done = gm.sample(states_dev, betas_dev, spb, seeds_dev, energies=energies_dev)
         assert done == R
         if world > 1:  # the path's only exchange: per-rank best (energy, global read index) from the library's argmin kernel
-            be, bi = ctx.argmin(energies_dev)
-            best_buf[0] = be
-            best_buf[1] = float(first_read + bi)
+            ctx.argmin_into(energies_dev, first_read, best_buf)      # device -> device: the all_gather's send buffer
             dist.all_gather(gathered, best_buf)
         if record:
             for k, v in st.as_dict().items():
@@ -363,6 +433,40 @@ def main():
                "api": "IsingModel(h, starts, ends, weights) + set_groups + sample(host states) [qa_model_from_ising + "
                       "qa_model_set_groups + qa_sa_sample_model]"}
 
+    # ---- e2e through the dimod-shaped sampler with return_samples='best_k': the state matrix is created (counter-based
+    # generator), annealed, ranked and reduced to k rows on the device -- what crosses PCIe is the model, the seeds, R energies
+    # and k samples.  Reported NEXT TO `e2e` (whose inputs and outputs are full host state matrices), not instead of it.
+    e2e_k = None
+    if not args.no_e2e:
+        from scrna_seq_qannealing_clustering_b200.sampler import B200SimulatedAnnealingSampler
+        smp = B200SimulatedAnnealingSampler(context=ctx)
+        kbest = 16
+
+        def step_best_k():
+            barrier()
+            t0 = time.perf_counter()
+            ss = smp.sample(model, num_reads=R * world, beta_schedule_type="custom", beta_schedule=betas, seed=args.seed,
+                            initial_states_generator="counter", return_samples="best_k", num_best=kbest)
+            dt = time.perf_counter() - t0
+            assert len(ss.info["energies"]) == R * world
+            return dt, ss
+
+        step_best_k()
+        elk = 0.0
+        k_steps = max(1, min(args.steps, 2))
+        for _ in range(k_steps):
+            dt, ss_k = step_best_k()
+            elk += dt
+        elk = allmax(elk)
+        h2d_k = (model.h.nbytes + model.starts.nbytes + model.ends.nbytes + model.weights.nbytes + seeds.nbytes + betas.nbytes
+                 + sum(np.asarray(g).nbytes for g in groups))
+        d2h_k = R * 8 + R * 4 + kbest * n
+        e2e_k = {"value": attempts_per_step_per_gpu * world * k_steps / elk, "unit": UNIT, "h2d_bytes_per_step": int(h2d_k),
+                 "d2h_bytes_per_step": int(d2h_k), "steps": k_steps, "ms_per_step": 1e3 * elk / k_steps, "num_best": kbest,
+                 "best_energy": float(ss_k.first.energy),
+                 "api": "B200SimulatedAnnealingSampler.sample(model, num_reads, beta_schedule, seed, initial_states_generator='counter', "
+                        "return_samples='best_k') -> SampleSet of the k best samples + info['energies']"}
+
     # ---- roofline of the dominant kernel (annealing), from the library's own CUDA events on its stream --------------
     peak, peak_src = peaks()
     launches = max(int(stats_acc.get("anneal_launches", 1)), 1)
@@ -411,6 +515,11 @@ def main():
                                 "energies_bitwise_identical_to_gpu": bool(np.array_equal(cpu_energies.view(np.uint64),
                                                                                          (gpu_e + model.offset).view(np.uint64)))}}
     best_weak = float(energies_dev.min().item() + model.offset)
+
+    # ---- BASELINE config 5: dense Gaussian-affinity 4-way model on the fp64 tensor-core kernel (every rank its own reads) ---
+    c5 = None
+    if not args.no_config5:
+        c5 = config5_block(args, ctx, dev, rank, world, allmax, threads if (rank == 0 and world == 1 and not args.no_cpu_baseline) else 0)
 
     # ---- the config AS STATED: job_reads x job_sweeps, reads split over the ranks (strong scaling), once ---------------
     job = None
@@ -494,9 +603,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed / args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, model, beta_range),
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(stats_acc.get("total_launches", 0)),
+            "clocks": clocks.summary(), "e2e": e2e, "e2e_best_k": e2e_k, "gpu_launches": int(stats_acc.get("total_launches", 0)),
             "roofline": roofline, "cpu_baseline": cpu, "best_energy": best_weak,
-            "full_job" if world == 1 else "strong": job,
+            "full_job" if world == 1 else "strong": job, "config5": c5,
         }
         emit(line)
     gm.close()

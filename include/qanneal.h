@@ -182,6 +182,9 @@ int qa_energy_argmin(qa_ctx *ctx, qa_model *model, int32_t num_reads, const int8
  */
 int qa_build_cut_balance(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
                          double gamma_factor, double k, qa_model **out, double *offset_out, double *gamma_out);
+/* qa_build_cut_linear    BQM_clustering.py:210-236 (clustering_bqm_2): k*cut + gamma*sum x, gamma = (W/n)*gamma_factor; sparse */
+int qa_build_cut_linear(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
+                        double gamma_factor, double k, qa_model **out, double *offset_out, double *gamma_out);
 int qa_build_subsampling(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
                          double gamma, double P, qa_model **out, double *offset_out);
 int qa_build_dqm_onehot(qa_ctx *ctx, int32_t n, int64_t m_edges, const int32_t *eu, const int32_t *ev, const double *w,
@@ -260,6 +263,9 @@ int qa_random_states(qa_ctx *ctx, uint64_t seed, int64_t first_read, int32_t num
 /* Lowest value and its first index (SampleSet.first; the per-rank half of the multi-GPU best-sample gather):
  * warp-shuffle min-reduction, ties to the lower index.  values: host or device pointer. */
 int qa_argmin(qa_ctx *ctx, int64_t count, const double *values, double *best_value, int64_t *best_index);
+/* The same reduction with its result left on the device: out_device[0] = lowest value, out_device[1] = (double)(index_offset +
+ * its first index) -- the 16-byte send buffer of the per-rank all_gather, filled without a host round trip. */
+int qa_argmin_device(qa_ctx *ctx, int64_t count, const double *values, int64_t index_offset, double *out_device);
 
 /* Test hook, host only (no device needed): the coupling slabs the replay kernel would get for a CSR in host memory
  * (adjacency order).  Returns 1 when the model fits the slab format, 0 when it does not, < 0 on error. */

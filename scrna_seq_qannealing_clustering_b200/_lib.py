@@ -99,6 +99,7 @@ SIGNATURES = {
     "qa_sa_sample_ising": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p, _i32, _i32, C.POINTER(QAStats)]),
     "qa_sa_sample_ising_batch": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p, C.POINTER(QAStats)]),
     "qa_build_cut_balance": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.c_double, C.c_double, C.POINTER(_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "qa_build_cut_linear": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.c_double, C.c_double, C.POINTER(_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qa_build_subsampling": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.c_double, C.c_double, C.POINTER(_p), C.POINTER(C.c_double)]),
     "qa_build_dqm_onehot": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _i32, C.POINTER(_p), C.POINTER(C.c_double)]),
     "qa_build_cqm_penalty": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _i32, C.c_double, C.c_double, C.POINTER(_p), C.POINTER(C.c_double)]),
@@ -109,6 +110,7 @@ SIGNATURES = {
     "qa_dev_copy": (C.c_int, [_p, _p, _p, _i64]),
     "qa_random_states": (C.c_int, [_p, C.c_uint64, _i64, _i32, _i32, _p]),
     "qa_argmin": (C.c_int, [_p, _i64, _p, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "qa_argmin_device": (C.c_int, [_p, _i64, _p, _i64, _p]),
     "qa_debug_pack_slabs": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "qa_snn_build": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, C.c_double, _i32, C.POINTER(_p)]),
     "qa_graph_num_edges": (_i64, [_p, _i32]),

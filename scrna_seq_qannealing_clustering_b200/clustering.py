@@ -154,20 +154,28 @@ def clustering_bqm(G, iteration, dirs, solver, gamma_factor, color=0, terminate_
 
 
 def clustering_bqm_2(G, iteration, dirs, solver, gamma_factor, color=0, terminate_on="once", size_limit=40, k=1,
-                     chain_strength=None, sampler=None, **sa_kwargs):
+                     chain_strength=None, sampler=None, device_build=None, **sa_kwargs):
     """2-way cut + linear gamma with the reference's recursion (BQM_clustering.py:206-350)."""
     if terminate_on not in ("min_size", "conf", "once"):
         raise NotImplementedError(f"clustering_bqm_2 has no terminate_on={terminate_on!r} branch (BQM_clustering.py:302-350)")
-    model = models.cut_linear_model(G, gamma_factor, k)
+    smp = _sampler(sampler)
+    if _on_device(smp, device_build):
+        model = smp.build_on_device("cut_linear", G, gamma_factor=gamma_factor, k=k)
+    else:
+        model = models.cut_linear_model(G, gamma_factor, k)
     sa_kwargs.setdefault("num_reads", 5000)  # BQM_clustering.py:240
-    response = _sample(_sampler(sampler), model, {"label": str(dirs.get("name", "")) + "_" + str(solver)}, sa_kwargs)
+    try:
+        response = _sample(smp, model, {"label": str(dirs.get("name", "")) + "_" + str(solver)}, sa_kwargs)
+    finally:
+        _close(model)
     S0, S1 = _split(G, response)
     go, how = bqm2_rule(terminate_on, len(S0), len(S1), response.record.energy, size_limit)
     _write_labels(G, S0, S1, "label" + str(iteration), how, color)
     if go:
         for part in (S0, S1):
             clustering_bqm_2(G.subgraph(part), iteration + 1, dirs, solver, gamma_factor, color=color + 20, terminate_on=terminate_on,
-                             size_limit=size_limit, k=k, chain_strength=chain_strength, sampler=sampler, **sa_kwargs)
+                             size_limit=size_limit, k=k, chain_strength=chain_strength, sampler=sampler, device_build=device_build,
+                             **sa_kwargs)
     return response
 
 
@@ -271,8 +279,8 @@ def recursive_bipartition_batched(G, gamma_factor, k=8.0, size_limit=40, iter_li
 
     Per level: ``qa_graph_split`` cuts the root graph into the level's sub-graphs on the device (``G.subgraph`` semantics: the
     parent's node and edge order), ``qa_build_cut_balance`` builds each one's structured model (k * cut + gamma * s(s - n) with
-    the balance term as a rank-1 group -- ``model="cut_balance"``) or the host builder its sparse ``clustering_bqm_2`` model
-    (``model="cut_linear"``), ``qa_model_concat`` joins them and ``qa_sa_sample_model_batch`` anneals ``num_reads`` reads of
+    the balance term as a rank-1 group -- ``model="cut_balance"``; ``qa_build_cut_linear``: the sparse ``clustering_bqm_2`` model --
+    ``model="cut_linear"``), ``qa_model_concat`` joins them and ``qa_sa_sample_model_batch`` anneals ``num_reads`` reads of
     every problem, each with the beta schedule of ITS OWN default range unless ``beta_range`` is given.  Initial states and
     per-read seeds are those a separate ``sampler.sample(model, seed=seed, num_reads=...)`` call per sub-graph would use, so
     the tree equals the one ``clustering_bqm(..., sampler=B200SimulatedAnnealingSampler(), seed=seed)`` builds call by call
@@ -283,7 +291,7 @@ def recursive_bipartition_batched(G, gamma_factor, k=8.0, size_limit=40, iter_li
     ``level_energies[i]`` their best energies.  ``write_labels=True`` also writes the reference's ``label<level>`` node
     attributes (random colours) into ``G``."""
     from . import schedule
-    from .engine import Context, IsingModel
+    from .engine import Context
 
     if model not in ("cut_balance", "cut_linear"):
         raise ValueError("model must be 'cut_balance' or 'cut_linear'")
@@ -310,8 +318,7 @@ def recursive_bipartition_batched(G, gamma_factor, k=8.0, size_limit=40, iter_li
                     if model == "cut_balance":
                         gm, off, _ = ctx.build_cut_balance(dg.device_graph(p), gamma_factor, k)
                     else:
-                        hm = models.cut_linear_model(dg.graph(p), gamma_factor, k)
-                        gm, off = IsingModel(ctx, hm.h, hm.starts, hm.ends, hm.weights), hm.offset
+                        gm, off, _ = ctx.build_cut_linear(dg.device_graph(p), gamma_factor, k)
                     gms.append(gm)
                     offsets.append(off)
                 if beta_range is None:   # every problem the default range of its own vectors, as separate sampler calls would

@@ -25,14 +25,7 @@
 // config 5, L2 resident); a thread's 4K words of a group are contiguous (K x LDG.128).
 // Cost: 2 * n_cells flops per attempt, independent of the acceptance rate -- bound by the fp64 tensor pipe.
 
-struct DenseDesc {
-    int32_t ncells;      // cells
-    int32_t ncp;         // cells padded to a multiple of 32 (padding rows / columns of W are zero)
-    int32_t K;           // cases per cell; variable v = cell*K + case
-    int32_t ngrp;        // ncp / 32
-    const double *W;     // [ncp][ncp] same-case coupling between cells, zero diagonal
-    double P;            // coupling between two cases of one cell
-};
+// (struct DenseDesc -- ncells, ncp, K, ngrp, W, P -- is declared in common.cuh: the model carries one)
 
 __device__ __forceinline__ void dn_dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -71,6 +64,10 @@ __device__ __forceinline__ void dn_block_fields(const DenseDesc &Dd, const uint3
 #pragma unroll
     for (int q = 0; q < K; ++q) wn[q] = __ldcg(wp + q);
     const int ngrp = Dd.ngrp;
+#ifdef DN_LOP3
+    unsigned sgn;
+    asm volatile("mov.u32 %0, 0x80000000;" : "=r"(sgn));   // opaque: kept in a register so that (x & sgn) ^ imm is ONE LOP3
+#endif
     for (int g = 0; g < ngrp; ++g) {
         double a[8];
         uint32_t w[NT];
@@ -97,7 +94,12 @@ __device__ __forceinline__ void dn_block_fields(const DenseDesc &Dd, const uint3
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 // bit -> +-1.0: high word 0xBFF00000 (-1.0) with the sign cleared when the bit is set
+#ifdef DN_LOP3
+                unsigned hi;
+                asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(hi) : "r"(w[t] << (31 - q)), "r"(sgn), "r"(0xBFF00000u));   // (a & b) ^ c
+#else
                 const unsigned hi = ((w[t] << (31 - q)) & 0x80000000u) ^ 0xBFF00000u;
+#endif
                 dn_dmma(C[t][0], C[t][1], a[q], __hiloint2double((int)hi, 0));
             }
         }
@@ -115,8 +117,11 @@ __device__ __forceinline__ void dn_store_fields(double *Fb, int lane, const doub
     }
 }
 
+#ifndef DN_MIN_CTAS
+#define DN_MIN_CTAS 2
+#endif
 template <int K>
-__global__ void __launch_bounds__(128, 2) k_anneal_dense(AnnealParams P, DenseDesc Dd) {
+__global__ void __launch_bounds__(128, DN_MIN_CTAS) k_anneal_dense(AnnealParams P, DenseDesc Dd) {
     constexpr int COLS = DnGeom<K>::COLS, LD = DnGeom<K>::LD;
     extern __shared__ __align__(16) double dn_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

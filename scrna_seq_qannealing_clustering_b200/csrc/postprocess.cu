@@ -7,9 +7,43 @@
 //   sample[(i, c)] / 'v_i,c' == 1 -> label                        -- one-hot decode of DQM / CQM   plot_and_save.py:46-63
 // With 10^5 reads of 10^5 variables the int8 state matrix is 13 GB: ordering, picking and decoding on the device means only
 // the k best samples (and the labels) cross PCIe.
-#pragma once
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+using namespace qa;
 
 namespace {
+
+// warp-shuffle min / argmin (lowest index wins ties, like a stable sort by energy -> SampleSet.first)
+__global__ void __launch_bounds__(1024) k_argmin(const double *energies, int64_t count, double *best_e, long long *best_i) {
+    __shared__ double se[32];
+    __shared__ long long si[32];
+    double e = INFINITY;
+    long long idx = 0x7fffffffffffffffll;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
+        const double x = energies[i];
+        if (x < e || (x == e && i < idx)) { e = x; idx = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oe = __shfl_xor_sync(FULL_MASK, e, off);
+        const long long oi = __shfl_xor_sync(FULL_MASK, idx, off);
+        if (oe < e || (oe == e && oi < idx)) { e = oe; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { se[threadIdx.x >> 5] = e; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        e = threadIdx.x < nw ? se[threadIdx.x] : INFINITY;
+        idx = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffffffffffffll;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double oe = __shfl_xor_sync(FULL_MASK, e, off);
+            const long long oi = __shfl_xor_sync(FULL_MASK, idx, off);
+            if (oe < e || (oe == e && oi < idx)) { e = oe; idx = oi; }
+        }
+        if (threadIdx.x == 0) { *best_e = e; *best_i = idx; }
+    }
+}
 
 // order-preserving map double -> uint64 (ascending); NaNs sort last
 __global__ void k_energy_keys(int32_t count, const double *e, unsigned long long *keys, int32_t *idx) {
@@ -120,6 +154,11 @@ __global__ void k_mark_heads(int32_t n, const int8_t *states, const unsigned lon
 }
 
 // stage `bytes` of a caller buffer (host or device) on the device; returns the device pointer to use
+__global__ void k_argmin_pack(const double *best_e, const long long *best_i, long long offset, double *out) {
+    out[0] = *best_e;
+    out[1] = (double)(*best_i + offset);   // read indices are < 2^53: exact
+}
+
 int stage_in(qa_ctx *ctx, DevBuf &buf, const void *p, size_t bytes, const void **dev) {
     if (is_device_ptr(p)) { *dev = p; return QA_OK; }
     int rc = ensure(buf, bytes);
@@ -130,6 +169,17 @@ int stage_in(qa_ctx *ctx, DevBuf &buf, const void *p, size_t bytes, const void *
 }
 
 }  // namespace
+
+namespace qa {
+
+int launch_argmin(qa_ctx *ctx, const double *d_values, int64_t count) {
+    k_argmin<<<1, 1024, 0, ctx->stream>>>(d_values, count, ctx->d_best_e, ctx->d_best_i);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return QA_OK;
+}
+
+}  // namespace qa
 
 extern "C" {
 
@@ -348,6 +398,25 @@ int qa_argmin(qa_ctx *ctx, int64_t count, const double *values, double *best_val
     QA_CUDA(cudaStreamSynchronize(ctx->stream));
     if (best_value) *best_value = be;
     if (best_index) *best_index = bi;
+    return QA_OK;
+}
+
+// the per-rank half of the multi-GPU best-sample exchange writes (best energy, GLOBAL read index) straight
+// into the device buffer the caller hands to its all_gather (16 bytes per rank) -- no host round trip between the reduction
+// and the collective.
+int qa_argmin_device(qa_ctx *ctx, int64_t count, const double *values, int64_t index_offset, double *out_device) {
+    if (!ctx || !out_device) return fail(QA_ERR_ARG, "null argument");
+    if (count < 1 || !values) return fail(QA_ERR_ARG, "need at least one value");
+    if (!is_device_ptr(out_device)) return fail(QA_ERR_ARG, "out_device must be device memory (the collective's send buffer)");
+    QA_CUDA(cudaSetDevice(ctx->device));
+    const void *d_v = nullptr;
+    int rc = stage_in(ctx, ctx->energies, values, (size_t)count * sizeof(double), &d_v);
+    if (rc) return rc;
+    k_argmin<<<1, 1024, 0, ctx->stream>>>((const double *)d_v, count, ctx->d_best_e, ctx->d_best_i);
+    k_argmin_pack<<<1, 1, 0, ctx->stream>>>(ctx->d_best_e, ctx->d_best_i, index_offset, out_device);
+    QA_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    QA_CUDA(cudaStreamSynchronize(ctx->stream));
     return QA_OK;
 }
 

@@ -10,6 +10,12 @@
 //   qa_sa_sample_model_batch  the batched launch on a resident model, optionally with one beta schedule PER PROBLEM (each
 //                             sub-graph gets the default range of its own model, as separate sampler calls would).
 
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+using namespace qa;
+
 namespace {
 
 // key of node v: its part, or num_parts when it is dropped

@@ -608,7 +608,6 @@ __host__ __device__ inline size_t rp_smem_bytes(int nw, int max_groups, unsigned
     const size_t pad = (sf - (smem_base + fixed) % sf) % sf;
     return fixed + pad + (size_t)nw * (sf + RP_PS_BYTES);
 }
-constexpr int QA_ERR_SMEM_BASE = -100;   // internal: the dynamic shared memory does not start where the host assumed
 
 template <int GROUPS, int SLOTS>
 __global__ void __launch_bounds__(RP_MAX_WARPS * 32, RP_MIN_CTAS) k_anneal_replay(AnnealParams P) {

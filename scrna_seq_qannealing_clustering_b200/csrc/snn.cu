@@ -25,7 +25,11 @@
 //   k_snn_count /  live entries with j > i -> edge list sorted by (u, v), local indices
 //   k_snn_emit
 
+#include "common.cuh"
+
 #include <cub/device/device_scan.cuh>
+
+using namespace qa;
 
 namespace {
 
@@ -321,27 +325,7 @@ int snn_scan(qa_ctx *ctx, int64_t count, const int32_t *in, int64_t *out, int64_
     return QA_OK;
 }
 
-// device scratch of one build, freed on every path
-struct SnnScratch {
-    std::vector<void *> ptrs;
-    ~SnnScratch() { for (void *p : ptrs) if (p) cudaFree(p); }
-    template <typename T> cudaError_t get(T **p, size_t count) {
-        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) ptrs.push_back(*p);
-        return e;
-    }
-};
-
 }  // namespace
-
-struct qa_graph {
-    qa_ctx *ctx = nullptr;
-    int32_t num_problems = 0;
-    std::vector<int64_t> point_off, edge_off;   // host copies [P + 1]
-    int32_t *eu = nullptr, *ev = nullptr;       // device, local indices, sorted by (problem, u, v)
-    double *w = nullptr;
-    int32_t *node_ids = nullptr;                // qa_graph_split: parent node of every local node, or null
-};
 
 extern "C" {
 

@@ -186,6 +186,14 @@ class Context:
         check(_lib.load().qa_argmin(self._h, count, ptr(values), C.byref(bv), C.byref(bi)))
         return float(bv.value), int(bi.value)
 
+    def argmin_into(self, values, index_offset: int, out):
+        """``argmin`` with the result left on the device: ``out`` (2 fp64, device) = (lowest value, index_offset + its first index) --
+        the send buffer of the per-rank all_gather."""
+        count = int(values.shape[0])
+        if not _is_tensor(values):
+            values = np.ascontiguousarray(values, dtype=np.float64)
+        check(_lib.load().qa_argmin_device(self._h, count, ptr(values), int(index_offset), ptr(out)))
+
     # -- SNN graphs on the device (qa_snn_build): the step before the path ------------------------
     def build_snn(self, X, k: int = 5, prune: float = 1.0 / 15.0, max_degree: Optional[int] = 15, offsets=None) -> "DeviceGraph":
         """Seurat-style SNN graph(s) of the rows of ``X`` ([points][dim] fp64, host array or device tensor) built by the
@@ -202,7 +210,7 @@ class Context:
                                        int(max_degree) if max_degree else 0, C.byref(hg)))
         return DeviceGraph(self, hg, int(off.shape[0] - 1))
 
-    # -- recursion driver on the device (csrc/recursion.cuh) --------------------------------------
+    # -- recursion driver on the device (csrc/recursion.cu) --------------------------------------
     def split_graph(self, graph, part, num_parts: int) -> "DeviceGraph":
         """``G.subgraph(part)`` for every part of a node partition at once (``qa_graph_split``): ``part[v]`` in [0, num_parts) or -1.
         ``graph`` is a host tuple ``(n, eu, ev, w)`` or ``DeviceGraph.device_graph(p)``."""
@@ -261,6 +269,14 @@ class Context:
         hm, off, gam = C.c_void_p(), C.c_double(), C.c_double()
         check(_lib.load().qa_build_cut_balance(self._h, n, m, ptr(eu), ptr(ev), ptr(w), float(gamma_factor), float(k), C.byref(hm),
                                                C.byref(off), C.byref(gam)))
+        return IsingModel._from_handle(self, hm), float(off.value), float(gam.value)
+
+    def build_cut_linear(self, graph, gamma_factor: float, k: float):
+        """``clustering_bqm_2`` model (BQM_clustering.py:210-236): k * cut + gamma * sum x.  -> (IsingModel, offset, gamma)"""
+        n, m, eu, ev, w = self._graph_args(graph)
+        hm, off, gam = C.c_void_p(), C.c_double(), C.c_double()
+        check(_lib.load().qa_build_cut_linear(self._h, n, m, ptr(eu), ptr(ev), ptr(w), float(gamma_factor), float(k), C.byref(hm),
+                                              C.byref(off), C.byref(gam)))
         return IsingModel._from_handle(self, hm), float(off.value), float(gam.value)
 
     def build_subsampling(self, graph, gamma: float, P: float = 1.0):

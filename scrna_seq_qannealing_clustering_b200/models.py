@@ -404,14 +404,16 @@ def cqm_model(G, num_of_clusters: int, min_size: int = 20, onehot_penalty: Optio
 # everything about a model EXCEPT its vectors: what the host needs when the vectors are built on the device (qa_build_*)
 # ------------------------------------------------------------------------------------------------
 def device_spec(kind: str, G, **p) -> Dict:
-    """Graph arrays, variable labels, penalties and ``meta`` of the model ``kind`` ('cut_balance', 'subsampling', 'dqm',
-    'cqm') -- O(n + m) numpy, no O(n^2) term, no Python loop over pairs.  The vectors come from ``Context.build_*``; they
+    """Graph arrays, variable labels, penalties and ``meta`` of the model ``kind`` ('cut_balance', 'cut_linear', 'subsampling',
+    'dqm', 'cqm') -- O(n + m) numpy, no O(n^2) term, no Python loop over pairs.  The vectors come from ``Context.build_*``; they
     are bit-identical to the host builders above (tests/test_gpu_builders.py)."""
     labels, eu, ev, w = graph_arrays(G)
     n = len(labels)
     graph = (n, eu.astype(np.int32), ev.astype(np.int32), w)
     if kind == "cut_balance":
         return {"graph": graph, "labels": labels, "meta": {"kind": "bqm", "builder": "cut_balance", "k": p.get("k", 8.0)}}
+    if kind == "cut_linear":
+        return {"graph": graph, "labels": labels, "meta": {"kind": "bqm", "builder": "cut_linear", "k": p.get("k", 1.0)}}
     if kind == "subsampling":
         return {"graph": graph, "labels": labels, "meta": {"kind": "bqm", "builder": "subsampling", "gamma": p["gamma"]}}
     K = int(p["num_of_clusters"])

@@ -159,14 +159,17 @@ class B200SimulatedAnnealingSampler:
         return _annotate_cqm(ss, model)
 
     def build_on_device(self, kind: str, G, **params) -> DeviceModel:
-        """The reference's model ``kind`` ('cut_balance' BQM_clustering.py:29-47, 'subsampling' QA_subsampling.py:26-35, 'dqm'
-        DQM_clustering.py:29-43, 'cqm' CQM_clustering.py:30-48) built by the ``qa_build_*`` kernels from the edge list: the
+        """The reference's model ``kind`` ('cut_balance' BQM_clustering.py:29-47, 'cut_linear' BQM_clustering.py:210-236,
+        'subsampling' QA_subsampling.py:26-35, 'dqm' DQM_clustering.py:29-43, 'cqm' CQM_clustering.py:30-48) built by the ``qa_build_*`` kernels from the edge list: the
         all-pairs / one-hot / slack terms never exist as host arrays.  The caller closes the returned model."""
         from . import models
         spec = models.device_spec(kind, G, **params)
         ctx = self.context
         if kind == "cut_balance":
             gm, off, gamma = ctx.build_cut_balance(spec["graph"], params["gamma_factor"], params.get("k", 8.0))
+            spec["meta"]["gamma"] = gamma
+        elif kind == "cut_linear":
+            gm, off, gamma = ctx.build_cut_linear(spec["graph"], params["gamma_factor"], params.get("k", 1.0))
             spec["meta"]["gamma"] = gamma
         elif kind == "subsampling":
             gm, off = ctx.build_subsampling(spec["graph"], params["gamma"], params.get("P", 1.0))

@@ -167,7 +167,7 @@ def random_spin_states(num_reads: int, n: int, seed: int) -> np.ndarray:
 
 
 def counter_spin_states(num_reads: int, n: int, seed: int, first_read: int = 0) -> np.ndarray:
-    """+-1 states from the library's counter-based generator (``qa_random_states``, csrc/postprocess.cuh::k_random_states):
+    """+-1 states from the library's counter-based generator (``qa_random_states``, csrc/postprocess.cu::k_random_states):
     spin (r, v) = bit (v & 63) of splitmix64-mix(seed, first_read + r, v >> 6), 1 -> -1.  A function of the GLOBAL read index:
     any sharding of the reads over GPUs draws the same states, and the device draws them without a host copy
     (``initial_states_generator='counter'``, an extension next to dimod's 'none' / 'tile' / 'random')."""

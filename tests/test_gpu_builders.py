@@ -57,6 +57,18 @@ def test_cut_balance(gpu_ctx, name):
 
 
 @pytest.mark.parametrize("name", list(GRAPHS))
+def test_cut_linear(gpu_ctx, name):
+    """clustering_bqm_2's sparse model (BQM_clustering.py:210-236), main.py:154's arguments k = 1, gamma_factor = 0.01."""
+    g = GRAPHS[name]()
+    model = models.cut_linear_model(g, 0.01, 1.0)
+    gm, off, gamma = gpu_ctx.build_cut_linear(g, 0.01, 1.0)
+    assert gamma == model.meta["gamma"]
+    assert_same_vectors(gm, model, off)
+    assert_same_anneal(gpu_ctx, gm, model)
+    gm.close()
+
+
+@pytest.mark.parametrize("name", list(GRAPHS))
 def test_subsampling(gpu_ctx, name):
     g = GRAPHS[name]()
     model = models.subsampling_model(g, 7.0)

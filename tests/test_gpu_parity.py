@@ -193,6 +193,13 @@ def test_energy_argmin_kernel(gpu_ctx, graph256):
     gm.close()
     assert np.array_equal(e.view(np.uint64), ref.view(np.uint64))
     assert bi == int(np.argmin(ref)) and be == ref.min()
+    # the same reduction with its result left on the device: the 16-byte send buffer of the per-rank all_gather
+    from scrna_seq_qannealing_clustering_b200.engine import DeviceBuffer
+    buf = DeviceBuffer(gpu_ctx, (2,), np.float64)
+    gpu_ctx.argmin_into(e, 1000, buf)
+    out = buf.download()
+    buf.close()
+    assert out[0] == ref.min() and out[1] == 1000 + int(np.argmin(ref))
     # the QUBO-form value (dimod bqm.energies) agrees to 1e-12 relative
     assert np.allclose(e + m.offset, m.energies(states), rtol=1e-12, atol=1e-9)
 

@@ -1,4 +1,4 @@
-"""Recursion driver on the device (csrc/recursion.cuh; reference: clustering_bqm calling itself on
+"""Recursion driver on the device (csrc/recursion.cu; reference: clustering_bqm calling itself on
 G.subgraph(S0) / G.subgraph(S1), Python_Functions/BQM_clustering.py:113-203): qa_graph_split, qa_model_concat,
 qa_sa_sample_model_batch, and the level-batched driver against the call-by-call recursion through the dimod-shaped sampler."""
 import json

@@ -1,4 +1,4 @@
-"""SNN graph construction on the device (csrc/snn.cuh, qa_snn_build) against the host specification
+"""SNN graph construction on the device (csrc/snn.cu, qa_snn_build) against the host specification
 snn.py and against the reference's own fixture graphs (R/benchmarks/graph_*.gexf, regenerated from the sklearn datasets of
 Benchmark.Rmd:33-55): identical edge sets, identical fp64 weights."""
 import time

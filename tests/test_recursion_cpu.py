@@ -61,6 +61,10 @@ class OracleBatchContext:
         m = models.cut_balance_model(graph, gamma_factor, k=k, structured=True)
         return _Model(m), m.offset, m.meta["gamma"]
 
+    def build_cut_linear(self, graph, gamma_factor, k):
+        m = models.cut_linear_model(graph, gamma_factor, k)
+        return _Model(m), m.offset, m.meta["gamma"]
+
     def concat_models(self, gms):
         return type("Batch", (), {"parts": list(gms), "close": lambda self: None})()
 
@@ -155,6 +159,16 @@ def test_batched_driver_builds_the_tree_of_the_call_by_call_recursion(rule, kw):
                                                             **kw)
     assert {c[0] for c in rec.calls} == {frozenset(part) for lv in levels for part in lv}
     assert ctx.calls == len(levels)
+
+
+def test_batched_driver_runs_the_cut_linear_model_too():
+    """clustering_bqm_2's sparse model (k * cut + gamma * sum x) through the same driver, `min_size` rule of bqm2_rule."""
+    X, _ = snn.gaussian_mixture_embedding(160, dim=8, centres=4, sep=9.0, seed=6)
+    G = snn.to_networkx(snn.snn_graph(X, k=10))
+    ctx = OracleBatchContext()
+    labels, levels, _ = clustering.recursive_bipartition_batched(G, 0.01, k=1.0, model="cut_linear", terminate_on="min_size", size_limit=30,
+                                                                 num_reads=16, num_sweeps=40, seed=2, context=ctx)
+    assert set(labels) == set(G.nodes) and ctx.calls == len(levels)
 
 
 def test_split_keeps_the_order_networkx_subgraphs_have():

@@ -1,4 +1,4 @@
-"""CPU tests of the replay kernel's host logic (csrc/qanneal.cu::pack_replay_slabs through the host-only C-ABI hook
+"""CPU tests of the replay kernel's host logic (csrc/anneal_replay.cu::pack_replay_slabs through the host-only C-ABI hook
 qa_debug_pack_slabs): block invariants of the coupling slabs, and -- the strong one -- a pure-Python replay that consumes
 ONLY the packed slabs in the kernel's two-phase order (pre parts of a block against the state at block start, then seq
 parts + decisions) and must reproduce the oracle's final states bit for bit.
