@@ -38,6 +38,7 @@ int launch_dense(Launch &L) {
     if (bps < 1) return fail(QA_ERR_CUDA, "dense kernel does not fit on an SM");
     const int64_t total_tiles = (reads_per_problem + 31) / 32;
     // every warp pulls 32-read tiles from a counter; no more CTAs than the tiles can fill (warps without a tile leave at once)
+    bps = std::min(bps, 2);   // 8 warps per SM beat 12 (measured, see dense.cuh)
     const int64_t grid = std::min<int64_t>((int64_t)bps * ctx->num_sms, (total_tiles + warps - 1) / warps);
     const int64_t stride = (int64_t)M->dn.ngrp * 32 * K;
     rc = ensure(ctx->sf, (size_t)grid * warps * stride * sizeof(uint32_t));

@@ -117,11 +117,14 @@ __device__ __forceinline__ void dn_store_fields(double *Fb, int lane, const doub
     }
 }
 
+// registers are bounded for 3 CTAs per SM (166 instead of 184): measured +19 % at EQUAL occupancy (8 warps per SM: 31.2 against
+// 26.2 TFLOP/s on config 5, profiles/r2_ab_dense_variants.log) -- ptxas schedules the operand preparation tighter; 12 warps per
+// SM are slower again (27.7), so the host keeps launching 2 CTAs per SM.  (K = 8 holds 64 accumulators: bounded for 2 CTAs.)
 #ifndef DN_MIN_CTAS
-#define DN_MIN_CTAS 2
+#define DN_MIN_CTAS 3
 #endif
 template <int K>
-__global__ void __launch_bounds__(128, DN_MIN_CTAS) k_anneal_dense(AnnealParams P, DenseDesc Dd) {
+__global__ void __launch_bounds__(128, (K >= 8 ? 2 : DN_MIN_CTAS)) k_anneal_dense(AnnealParams P, DenseDesc Dd) {
     constexpr int COLS = DnGeom<K>::COLS, LD = DnGeom<K>::LD;
     extern __shared__ __align__(16) double dn_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
