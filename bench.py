@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--sweeps", type=int, default=50,
                     help="points of the geometric beta schedule per step (the full config-3 job is 1000; the per-attempt "
                          "phase mix, hence attempts/s, is the same for any length over the same beta range)")
+    ap.add_argument("--size-penalty", type=float, default=None,
+                    help="CQM size penalty B (default: onehot_penalty / cells, the library's default; 1.0 reproduces the round-1 "
+                         "workload, whose binary slack freezes and leaves no read feasible)")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (0: 2 x host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -68,7 +71,7 @@ def parse_args():
 def build_workload(args):
     from scrna_seq_qannealing_clustering_b200 import models, schedule, snn
     graph, _ = snn.synthetic_snn(args.cells, k=5, dim=15, centres=args.clusters, seed=0)
-    model = models.cqm_model(graph, args.clusters, min_size=20)
+    model = models.cqm_model(graph, args.clusters, min_size=20, size_penalty=getattr(args, "size_penalty", None))
     # beta range from the explicit couplers (one-hot + objective), not from the rank-1 size penalty: neal's default on
     # the penalty would start at beta ~ 1e-8 and spend most sweeps at ~100 % acceptance (SURVEY.md hard part 4)
     beta_range = schedule.default_ising_beta_range(model.h, model.starts, model.ends, model.weights, None)

@@ -70,7 +70,7 @@ extern "C" {
 int qa_model_enable_dense(qa_model *M, int32_t K) {
     if (!M) return fail(QA_ERR_ARG, "null model");
     if (K != 1 && K != 2 && K != 4 && K != 8) return fail(QA_ERR_ARG, "dense form: cases per cell must be 1, 2, 4 or 8");
-    if (M->num_problems != 1 || M->ngroups != 0) return fail(QA_ERR_ARG, "dense form needs a single problem without groups");
+    if (M->num_problems != 1 || M->ngroups != 0) return 0;   // batched models and rank-1 group terms are outside the dense form
     const int64_t n = M->n_total;
     if (n == 0 || n % K != 0) return fail(QA_ERR_ARG, "number of variables is not a multiple of the cases per cell");
     qa_ctx *ctx = M->ctx;

@@ -359,7 +359,7 @@ def cqm_model(G, num_of_clusters: int, min_size: int = 20, onehot_penalty: Optio
                                                    ->  B * (N_j - min_size - sum_b c_b*sigma_jb)^2, binary slack sigma
     Variable (cell i, cluster p) -> i*K + p with label 'v_{i},{p}' (i = node label, or ``subindex`` for cqm_2);
     slack sigma_jb -> n*K + j*nb + b with label 'slack_cluster_size{j}_{b}'.  A and B are ours (Leap's CQM solver
-    handles constraints natively) and are reported in ``meta``.
+    handles constraints natively; defaults A = max degree + max sum |2w| + 1, B = A / n) and are reported in ``meta``.
     """
     labels, eu, ev, w = graph_arrays(G)
     n, K = len(labels), int(num_of_clusters)
@@ -367,7 +367,11 @@ def cqm_model(G, num_of_clusters: int, min_size: int = 20, onehot_penalty: Optio
     deg = _edge_order_sum(n, eu, ev, np.ones(len(w)))
     wdeg = _edge_order_sum(n, eu, ev, np.abs(2 * w))
     A = float(deg.max() + wdeg.max() + 1.0) if onehot_penalty is None else float(onehot_penalty)
-    B = 1.0 if size_penalty is None else float(size_penalty)
+    # size penalty: scaled so that one cell changing cluster moves it by at most 2*B*n = 2*A, the one-hot scale.  With B = 1
+    # the binary slack bits (coefficients up to ~n/2) freeze at every temperature the objective cares about, the cell bits are
+    # slaved to them and no read ends one-hot (measured: 0 of 100 000 reads on config 3); with B = A/n every read of the same
+    # job is feasible.  The reference never meets this: Leap's CQM solver handles constraints natively.
+    B = A / max(n, 1) if size_penalty is None else float(size_penalty)
     coeffs = slack_coefficients(n - min_size)
     nb = len(coeffs)
     names = labels if subindex is None else list(subindex)
@@ -398,6 +402,30 @@ def cqm_model(G, num_of_clusters: int, min_size: int = 20, onehot_penalty: Optio
             "onehot_penalty": A, "size_penalty": B, "slack_coefficients": coeffs, "num_cell_variables": nx_}
     model = LoweredModel(h, r, c, J, off + A * n, var_labels, groups, meta)
     return model if structured else model.materialise()
+
+
+def consistent_slack(states: np.ndarray, meta: Dict) -> np.ndarray:
+    """Set the slack bits of +-1 CQM states (in place) to the binary encoding of ``max(N_j - min_size, 0)``, N_j = number of
+    cells whose bit for cluster j is set, so that the size penalty B*(N_j - min_size - slack_j)^2 starts at zero.
+
+    Why: with uniformly random slack bits the penalty starts at ~(n/2)^2 per cluster and the high slack bits (a flip moves it by
+    ~c_b * n) are frozen at every temperature the objective cares about; the cell bits are then slaved to the random slack values
+    and no read ends one-hot (measured on config 3: 0 of 100 000 reads).  The reference never meets this -- it hands the CQM to
+    Leap's hybrid solver, which treats constraints natively.  Used by ``sample_cqm`` for generated initial states."""
+    K = int(meta["num_cases"])
+    nx = int(meta["num_cell_variables"])
+    coeffs = np.asarray(meta["slack_coefficients"], dtype=np.int64)
+    nb = len(coeffs)
+    if nb == 0:
+        return states
+    cells = nx // K
+    counts = (states[:, :nx].reshape(len(states), cells, K) > 0).sum(axis=1).astype(np.int64)          # [R][K]
+    v = np.clip(counts - int(meta["min_size"]), 0, int(coeffs.sum()))
+    for b in np.argsort(-coeffs, kind="stable"):          # greedy from the largest coefficient: exact for dimod's encoding
+        take = v >= coeffs[b]
+        v = v - coeffs[b] * take
+        states[:, nx + np.arange(K) * nb + b] = np.where(take, 1, -1).astype(states.dtype)
+    return states
 
 
 # ------------------------------------------------------------------------------------------------
@@ -442,7 +470,7 @@ def device_spec(kind: str, G, **p) -> Dict:
         deg = _edge_order_sum(n, eu, ev, np.ones(len(w)))
         wdeg = _edge_order_sum(n, eu, ev, np.abs(2 * w))
         A = float(deg.max() + wdeg.max() + 1.0) if p.get("onehot_penalty") is None else float(p["onehot_penalty"])
-        B = 1.0 if p.get("size_penalty") is None else float(p["size_penalty"])
+        B = A / max(n, 1) if p.get("size_penalty") is None else float(p["size_penalty"])      # see cqm_model
         coeffs = slack_coefficients(n - min_size)
         names = labels if p.get("subindex") is None else list(p["subindex"])
         var_labels: List[Hashable] = [f"v_{names[i]},{q}" for i in range(n) for q in range(K)]

@@ -142,11 +142,13 @@ class B200SimulatedAnnealingSampler:
         return _decode_discrete(ss, model, dqm if isinstance(dqm, DiscreteQuadraticModel) else None)
 
     def sample_cqm(self, cqm, onehot_penalty: Optional[float] = None, constraint_penalty: Optional[float] = None,
-                   **parameters) -> SampleSet:
+                   slack_init: str = "consistent", **parameters) -> SampleSet:
         """``LeapHybridCQMSampler().sample_cqm`` stand-in (CQM_clustering.py:53,89): constraints lowered to penalties.
 
         Rows keep the binary variables ('v_{i},{k}' and slack bits); record fields ``is_feasible`` (one-hot and
         minimum-size constraints satisfied by the cell variables) and ``objective`` are added.
+        ``slack_init='consistent'`` (default): generated initial states get slack bits that encode their own cluster sizes, so
+        the size penalty starts at zero (``models.consistent_slack``); ``'random'``: dimod's uniformly random states.
         """
         from .cqm import ConstrainedQuadraticModel
         if isinstance(cqm, (LoweredModel, DeviceModel)):
@@ -155,7 +157,18 @@ class B200SimulatedAnnealingSampler:
             model = cqm.to_lowered(onehot_penalty, constraint_penalty)
         else:
             raise TypeError("sample_cqm expects a ConstrainedQuadraticModel or a LoweredModel built by models.cqm_model")
+        meta = getattr(model, "meta", {})
+        if (slack_init == "consistent" and parameters.get("initial_states") is None and "slack_coefficients" in meta
+                and parameters.get("initial_states_generator", "random") == "random"):
+            # generated initial states: random cell bits, slack bits encoding max(N_j - min_size, 0) (models.consistent_slack)
+            from .models import consistent_slack
+            seed = schedule.resolve_seed(parameters.get("seed"))
+            parameters["seed"] = seed
+            init = schedule.random_spin_states(int(parameters.get("num_reads") or 1), model.num_variables, seed)
+            parameters["initial_states"] = ((consistent_slack(init, meta) + 1) // 2, model.labels)
+            parameters["num_reads"] = None
         ss = self.sample(model, **parameters)
+        ss.info["slack_init"] = slack_init
         return _annotate_cqm(ss, model)
 
     def build_on_device(self, kind: str, G, **params) -> DeviceModel:

@@ -126,6 +126,14 @@ def test_structure_check_rejects_other_models(ctx):
         assert gm.enable_dense(4) is False          # but its couplers do not have the k-way Kronecker form
     finally:
         gm.close()
+    # rank-1 group terms are outside the dense form: not an error, just "no"
+    mg = models.cqm_model(g, 4, min_size=5)
+    gm = IsingModel(ctx, mg.h, mg.starts, mg.ends, mg.weights)
+    try:
+        gm.set_groups(*mg.groups.astuple())
+        assert gm.enable_dense(4) is False
+    finally:
+        gm.close()
     # case-dependent inter-cell coupling: rejected
     m4 = _affinity_model(40, 4)
     w = m4.weights.copy()

@@ -221,3 +221,25 @@ def test_dwave_samplers_default_beta_range_rule():
     _, cold1 = schedule.default_ising_beta_range_samplers(h, irow, icol, q, scale_T_with_N=False)
     assert cold1 == pytest.approx(np.log(1 / 0.01) / 0.5)
     assert schedule.default_ising_beta_range_samplers(np.zeros(3), np.zeros(0, int), np.zeros(0, int), np.zeros(0)) == (1.0, 1.0)
+
+
+def test_consistent_slack_makes_the_size_penalty_start_at_zero():
+    """models.consistent_slack (used by sample_cqm for generated initial states): slack bits encode max(N_j - min_size, 0)
+    exactly, for dimod's binary encoding with its odd last coefficient, and clamp at the ends of the range."""
+    import numpy as np
+    from scrna_seq_qannealing_clustering_b200 import models, schedule, snn
+    g = snn.synthetic_snn(300, k=5, seed=2)[0]
+    m = models.cqm_model(g, 3, min_size=20)
+    assert m.meta["size_penalty"] == m.meta["onehot_penalty"] / 300      # default B = A / n
+    K, nx = 3, m.meta["num_cell_variables"]
+    co = np.array(m.meta["slack_coefficients"])
+    st = schedule.random_spin_states(40, m.num_variables, 1)
+    st[0, :nx] = -1                                   # empty clusters: below min_size -> slack 0
+    st[1, :nx] = 1                                    # every bit set: N_j = n -> slack n - min_size (the top of the range)
+    models.consistent_slack(st, m.meta)
+    x = (st + 1) // 2
+    N = x[:, :nx].reshape(40, -1, K).sum(axis=1)
+    slack = x[:, nx:].reshape(40, K, len(co)) @ co
+    assert np.array_equal(slack, np.clip(N - 20, 0, co.sum()))
+    assert (slack[0] == 0).all() and (slack[1] == 300 - 20).all()
+    assert set(np.unique(st)) <= {-1, 1}

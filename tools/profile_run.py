@@ -21,6 +21,7 @@ ap.add_argument("--sweeps", type=int, default=20)
 ap.add_argument("--cells", type=int, default=0)
 ap.add_argument("--clusters", type=int, default=0)
 ap.add_argument("--kernel", type=int, default=0)
+ap.add_argument("--size-penalty", type=float, default=None)
 a = ap.parse_args()
 a.seed = 1234
 import torch  # noqa: E402
