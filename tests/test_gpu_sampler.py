@@ -124,6 +124,20 @@ def test_clustering_functions(sampler):
     assert (sizes >= 20).all() and (sizes.sum(axis=1) == 256).all()
 
 
+def test_clustering_cqm_defaults_give_feasible_reads(sampler):
+    """The product's defaults (one-hot penalty A, size penalty B = A / n, slack bits initialised consistently with the cell bits)
+    must leave SA-reachable feasible states: with round 1's B = 1 the binary slack froze and no read ended one-hot."""
+    G = snn.to_networkx(snn.synthetic_snn(1024, k=5, seed=4)[0])
+    cq = qa.clustering_cqm(G, 4, sampler=sampler, num_reads=64, num_sweeps=300, seed=7)
+    assert cq.info["slack_init"] == "consistent"
+    assert cq.info["size_penalty"] == pytest.approx(cq.info["onehot_penalty"] / 1024)
+    assert cq.record.is_feasible.mean() >= 0.9
+    sizes = cq.record.cluster_sizes[cq.record.is_feasible]
+    assert (sizes >= 20).all() and (sizes.sum(axis=1) == 1024).all()
+    hard = qa.clustering_cqm(G, 4, sampler=sampler, num_reads=64, num_sweeps=300, seed=7, size_penalty=1.0)
+    assert hard.record.is_feasible.mean() <= cq.record.is_feasible.mean()
+
+
 def test_generic_dqm_and_cqm_objects(sampler):
     d = qa.DiscreteQuadraticModel()
     for v in range(6):
