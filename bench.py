@@ -564,8 +564,14 @@ def main():
         jenergies = torch.empty(Rj, dtype=torch.float64, device=dev)
         jseeds_dev = torch.from_numpy(jseeds.view(np.int64)).to(dev)
         barrier()
-        _, jst, jdone = gm.sample(jstates, torch.from_numpy(jbetas).to(dev), jspb, jseeds_dev, energies=jenergies)
+        with ClockSampler(local_rank) as jclocks:      # a two-minute launch: clocks and throttle reasons of THIS leg, per rank
+            _, jst, jdone = gm.sample(jstates, torch.from_numpy(jbetas).to(dev), jspb, jseeds_dev, energies=jenergies)
         assert jdone == Rj
+        jck = jclocks.summary()
+        jck["sm_mhz_min_over_ranks"] = -allmax(-(jck["sm_mhz"] or 0.0))
+        jck["slowest_rank_seconds"] = allmax(jst.ms_total * 1e-3)
+        jck["fastest_rank_seconds"] = -allmax(-jst.ms_total * 1e-3)
+        jck["throttled_ranks"] = allsum(1.0 if jck["reasons"] else 0.0)
         t_job = allmax(jst.ms_total * 1e-3)
         job_attempts = float(n) * job_sweeps * args.job_reads
         cells = len(model.meta["cells"])
@@ -582,7 +588,8 @@ def main():
                "feasible_fraction": feasible / args.job_reads, "onehot_satisfied_fraction": onehot_ok / args.job_reads,
                "mean_cells_not_onehot_per_read": bad_cells / args.job_reads, "cells": cells,
                "mean_clusters_below_min_size_per_read": small_clusters / args.job_reads,
-               "best_energy": best_job, "kernel_ms": allmax(jst.ms_anneal), "vs_weak_value_per_gpu": (job_attempts / t_job / world) / rate}
+               "best_energy": best_job, "kernel_ms": allmax(jst.ms_anneal), "vs_weak_value_per_gpu": (job_attempts / t_job / world) / rate,
+               "clocks": jck}
         if ncj:
             # the CPU arm on the first reads of the job: the converged target of the time-to-best-energy figure, and one more
             # parity check at the full schedule length

@@ -246,8 +246,12 @@ int launch_replay(Launch &L) {
         nw = 1;
         while (nw < RP_MAX_WARPS && nw < tpp) nw *= 2;
         while (nw > 1 && rp_smem_bytes(nw, mg, ctx->rp_smem_base, M->rp_slots) > (size_t)(226 * 1024 / RP_MIN_CTAS - 1024)) nw /= 2;   // RP_MIN_CTAS CTAs per SM
-        // few tiles: prefer narrower CTAs on every SM to full CTAs on some of them
-        while (nw > 1 && (int64_t)P * ((tpp + nw - 1) / nw) < 2 * (int64_t)ctx->num_sms) nw /= 2;
+        // less than one full wave of 8-warp CTAs: 4-warp CTAs (3 per SM) balance the SMs better -- measured on config 3
+        // (profiles/r2_probe_strong_scaling_read_counts.log): 50 000 reads 7.4e10 against 6.8e10 with 8 warps, 25 000 and 12 500
+        // reads within 1 % of the best choice; 1- and 2-warp CTAs are residency-limited by the slab ring's shared memory
+        if ((int64_t)P * tpp < (int64_t)RP_MIN_CTAS * ctx->num_sms * RP_MAX_WARPS && nw > 4) nw = 4;
+        // very few tiles: prefer narrower CTAs on every SM to wide CTAs on some of them
+        while (nw > 1 && (int64_t)P * ((tpp + nw - 1) / nw) < (int64_t)ctx->num_sms) nw /= 2;
     }
     const int64_t gpp = (tpp + nw - 1) / nw;
     const int64_t total_items = (int64_t)P * gpp;
