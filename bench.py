@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-full-job", action="store_true", help="skip the 100 000 reads x 1000 sweeps job (full_job / strong blocks)")
     ap.add_argument("--job-reads", type=int, default=100000, help="reads of the stated job (split over the ranks)")
     ap.add_argument("--job-sweeps", type=int, default=1000)
+    ap.add_argument("--job-share", default="", help="development, N = 1 only: 'r/w' anneals the share of rank r of w ranks")
     ap.add_argument("--no-config5", action="store_true", help="skip the dense tensor-core block (BASELINE config 5)")
     ap.add_argument("--c5-reads", type=int, default=37888, help="reads per GPU of the config-5 block (148 SMs x 8 warps x 32 reads)")
     ap.add_argument("--c5-sweeps", type=int, default=20)
@@ -540,8 +541,11 @@ def main():
         if not args.no_e2e:
             del host_states, hs
         torch.cuda.empty_cache()
-        lo = rank * args.job_reads // world
-        hi = (rank + 1) * args.job_reads // world
+        srank, sworld = rank, world
+        if args.job_share and world == 1:      # development: anneal the share rank r of w would get (same reads, seeds, initial states)
+            srank, sworld = (int(x) for x in args.job_share.split("/"))
+        lo = srank * args.job_reads // sworld
+        hi = (srank + 1) * args.job_reads // sworld
         Rj = hi - lo
         # shorten the job when it would not fit the wall-clock budget (the rate does not depend on the schedule length: same
         # beta range, same phase mix -- measured, see `full_job.value` against `value`)
@@ -556,7 +560,7 @@ def main():
         jbetas, jspb = schedule.make_beta_schedule(beta_range, job_sweeps, 1, "geometric")
         jseeds = schedule.per_read_seeds(args.seed + 1, Rj, first_read=lo)
         g = torch.Generator(device=dev)
-        g.manual_seed(args.seed + 17 + rank)
+        g.manual_seed(args.seed + 17 + srank)
         jstates = torch.randint(0, 2, (Rj, n), dtype=torch.int8, device=dev, generator=g)
         jstates.mul_(2).sub_(1)
         ncj = min(Rj, 2 * threads) if (rank == 0 and not args.no_cpu_baseline) else 0
