@@ -311,6 +311,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # The path's only exchange is 16 bytes per rank and step.  With NCCL's peer-to-peer transport enabled (peer mappings of
+        # the other ranks' memory), the annealing kernel of rank 0 ran 45 % longer in the part-filled strong leg (117 s against
+        # 83 s for the same 50 000-read share; measured four ways: torchrun default, NVLS off, P2P off, two independent
+        # processes -- profiles/r2_strong_leg_n2_investigation.md).  Default to NCCL's shared-memory transport; an explicit
+        # NCCL_P2P_DISABLE in the environment wins.
+        os.environ.setdefault("NCCL_P2P_DISABLE", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -576,6 +582,11 @@ def main():
         jck["slowest_rank_seconds"] = allmax(jst.ms_total * 1e-3)
         jck["fastest_rank_seconds"] = -allmax(-jst.ms_total * 1e-3)
         jck["throttled_ranks"] = allsum(1.0 if jck["reasons"] else 0.0)
+        if world > 1:      # who was slow: kernel seconds of every rank, in rank order
+            mine = torch.tensor([jst.ms_anneal * 1e-3], dtype=torch.float64, device=dev)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            jck["kernel_seconds_by_rank"] = [float(x.item()) for x in every]
         t_job = allmax(jst.ms_total * 1e-3)
         job_attempts = float(n) * job_sweeps * args.job_reads
         cells = len(model.meta["cells"])
