@@ -1,4 +1,4 @@
-// postprocess.cuh -- SampleSet post-processing on the device.  Included by qanneal.cu.
+// postprocess.cu -- SampleSet post-processing on the device.  
 //
 // What the reference does with a SampleSet after the sampler call (all on the host, one sample at a time):
 //   response.data(fields=['sample','energy','num_occurrences'])  -- energy-sorted iteration       BQM_clustering.py:93,281,397

@@ -1,4 +1,4 @@
-// recursion.cuh -- device side of the recursive bipartition driver (reference: the recursion of
+// recursion.cu -- device side of the recursive bipartition driver (reference: the recursion of
 // clustering_bqm / clustering_bqm_2, Python_Functions/BQM_clustering.py:113-203, 302-350, which calls itself on
 // G.subgraph(S0) and G.subgraph(S1)).
 //

@@ -1,4 +1,4 @@
-// snn.cuh -- shared-nearest-neighbour graph construction on the device: the step BEFORE the hot path.
+// snn.cu -- shared-nearest-neighbour graph construction on the device: the step BEFORE the hot path.
 //
 // Reference recipe (Seurat FindNeighbors as used by R/pbmc3k/Pbmc3k_general_data_preparation.Rmd:47-75 and
 // R/benchmarks/Benchmark.Rmd:150-166; validated against the shipped R/benchmarks/graph_*.gexf fixtures):

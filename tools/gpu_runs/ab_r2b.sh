@@ -1,4 +1,4 @@
-source tools/ab_variants.sh r2b_ab.log true
+source tools/gpu_runs/ab_variants.sh r2b_ab.log true
 run base base --permille 10,5,7,15
 run la2 la2 --permille 10
 run pf64 pf64 --permille 10

@@ -1,4 +1,4 @@
-source tools/ab_variants.sh r2c_ab.log true
+source tools/gpu_runs/ab_variants.sh r2c_ab.log true
 run s2w4 s2w4 --permille 10 --warps 4
 run s3w5 s3w5 --permille 10 --warps 5 --reads 71040
 run s3w8 s3w8 --permille 10

@@ -1,4 +1,4 @@
-source tools/ab_variants.sh r2d_ab.log true
+source tools/gpu_runs/ab_variants.sh r2d_ab.log true
 run nb nb --permille 10
 run nb_pf16 nb_pf16 --permille 10
 run nb_pf16_la6 nb_pf16_la6 --permille 10
