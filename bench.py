@@ -276,6 +276,8 @@ def main_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{reads} reads x {len(betas) * spb} sweeps x {model.num_variables} vars per step, OpenMP over reads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "`config` names the workload of the GPU arm; a CPU step anneals the bounded sample in cpu_baseline.sample of that "
+                "workload (same model, schedule, seeding rule) -- a rate, so the read count does not enter the metric",
     }
     emit(line)
 
