@@ -6,6 +6,10 @@ using namespace qa;
 
 namespace {
 
+#ifndef QA_EN_BATCH
+#define QA_EN_BATCH 16
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // energies: neal get_state_energy(), one thread per read, reads on lanes (coalesced packedT loads)
 // ------------------------------------------------------------------------------------------------
@@ -38,20 +42,22 @@ __global__ void __launch_bounds__(128) k_energy(const ProblemDesc *descs) {
         }
     }
     // couplers in the caller's order: the additions are one dependent chain, the (random-row) spin loads are not -- issue
-    // them eight couplers at a time
+    // them QA_EN_BATCH couplers at a time.  Measured on config 3 (75 776 reads): 228 ms with batches of 8, 217 ms with 16, 240 ms
+    // with 32; keeping the row's word in a register across the couplers that share it (a uniform branch in the add chain) is
+    // slower, 261 ms.
     int64_t e = 0;
-    for (; e + 8 <= D.m; e += 8) {
-        uint32_t bu[8], bv[8];
-        double wt[8];
+    for (; e + QA_EN_BATCH <= D.m; e += QA_EN_BATCH) {
+        uint32_t bu[QA_EN_BATCH], bv[QA_EN_BATCH];
+        double wt[QA_EN_BATCH];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < QA_EN_BATCH; ++q) {
             const int u = __ldg(D.starts + e + q), v = __ldg(D.ends + e + q);
             wt[q] = __ldg(D.w + e + q);
             bu[q] = pk[(int64_t)(u >> 5) * stride] >> (u & 31);
             bv[q] = pk[(int64_t)(v >> 5) * stride] >> (v & 31);
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) E += ((bu[q] ^ bv[q]) & 1u) ? -wt[q] : wt[q];  // state[u]*w*state[v]
+        for (int q = 0; q < QA_EN_BATCH; ++q) E += ((bu[q] ^ bv[q]) & 1u) ? -wt[q] : wt[q];  // state[u]*w*state[v]
     }
     for (; e < D.m; ++e) {
         const int u = __ldg(D.starts + e), v = __ldg(D.ends + e);
