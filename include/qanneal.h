@@ -143,12 +143,15 @@ int qa_sa_sample_model(qa_ctx *ctx, qa_model *model, int32_t num_reads, int8_t *
                        int32_t mode, qa_interrupt_fn interrupt, void *interrupt_user,
                        qa_stats *stats_out);
 
-/* One-shot form mirroring neal's general_simulated_annealing (model built and freed inside). */
+/* One-shot form mirroring neal's general_simulated_annealing, argument for argument (model built and freed inside):
+ * interrupt / interrupt_user are neal's interrupt_callback / interrupt_function (may be NULL); the return value is the number
+ * of reads completed. */
 int qa_sa_sample_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const int32_t *starts,
                        const int32_t *ends, const double *weights, int32_t num_reads,
                        int8_t *states_inout, double *energies_out, int32_t num_betas,
                        const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds,
-                       int32_t seed_mode, int32_t mode, qa_stats *stats_out);
+                       int32_t seed_mode, int32_t mode, qa_interrupt_fn interrupt, void *interrupt_user,
+                       qa_stats *stats_out);
 
 /* Many independent problems in one launch (QA_subsampling.py:24 called per sub-graph).
  * Problem p owns variables [var_offsets[p], var_offsets[p+1]) of h and couplers

@@ -349,7 +349,7 @@ int qa_sa_sample_model(qa_ctx *ctx, qa_model *model, int32_t num_reads, int8_t *
 int qa_sa_sample_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const int32_t *starts, const int32_t *ends,
                        const double *weights, int32_t num_reads, int8_t *states_inout, double *energies_out, int32_t num_betas,
                        const double *beta_schedule, int32_t sweeps_per_beta, const uint64_t *seeds, int32_t seed_mode,
-                       int32_t mode, qa_stats *stats_out) {
+                       int32_t mode, qa_interrupt_fn interrupt, void *interrupt_user, qa_stats *stats_out) {
     if (!ctx) return fail(QA_ERR_ARG, "null context");
     cudaEvent_t b0 = nullptr, b1 = nullptr;
     QA_CUDA(cudaSetDevice(ctx->device));
@@ -362,7 +362,7 @@ int qa_sa_sample_ising(qa_ctx *ctx, int32_t n, const double *h, int64_t m, const
     cudaEventRecord(b1, ctx->stream);
     if (rc == QA_OK) {
         rc = sample_common(ctx, M, num_reads, states_inout, energies_out, num_betas, beta_schedule, sweeps_per_beta, seeds,
-                           seed_mode, mode, nullptr, nullptr, stats_out);
+                           seed_mode, mode, interrupt, interrupt_user, stats_out);
         if (rc >= 0 && stats_out) {
             cudaEventSynchronize(b1);
             stats_out->ms_build = elapsed(b0, b1);

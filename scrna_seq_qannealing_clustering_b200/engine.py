@@ -305,7 +305,7 @@ class Context:
 
     # -- neal's general_simulated_annealing, one shot, host or device buffers --------------------
     def sample_ising(self, h, starts, ends, weights, states, beta_schedule, sweeps_per_beta, seeds,
-                     seed_mode=_lib.QA_SEED_PER_READ, mode=_lib.QA_MODE_REFERENCE, energies=None):
+                     seed_mode=_lib.QA_SEED_PER_READ, mode=_lib.QA_MODE_REFERENCE, energies=None, interrupt_function=None):
         h = _as(h, np.float64, "h")
         starts = _as(starts, np.int32, "starts")
         ends = _as(ends, np.int32, "ends")
@@ -318,11 +318,14 @@ class Context:
         num_reads = int(states.shape[0]) if n else 0
         if energies is None:
             energies = np.empty(num_reads, dtype=np.float64)
+        cb = None
+        if interrupt_function is not None:
+            cb = _lib.INTERRUPT_FN(lambda _u: 1 if interrupt_function() else 0)
         st = QAStats()
         done = check(_lib.load().qa_sa_sample_ising(
             self._h, n, ptr(h), m, ptr(starts), ptr(ends), ptr(weights), num_reads, ptr(states), ptr(energies),
             int(beta_schedule.shape[0]), ptr(beta_schedule), int(sweeps_per_beta), ptr(seeds), int(seed_mode), int(mode),
-            C.byref(st)))
+            C.cast(cb, C.c_void_p) if cb is not None else None, None, C.byref(st)))
         return energies, st, done
 
     def sample_ising_batch(self, var_offsets, coupler_offsets, h, starts, ends, weights, reads_per_problem, states,

@@ -180,6 +180,21 @@ def test_one_shot_host_buffers_like_neal(gpu_ctx, graph256):
     e, st, done = gpu_ctx.sample_ising(m.h, m.starts, m.ends, m.weights, states, betas, spb, seeds)
     assert done == 40 and np.array_equal(states, ref) and np.array_equal(e.view(np.uint64), ref_e.view(np.uint64))
     assert st.total_launches >= 3 and st.ms_anneal > 0
+    # neal's interrupt_callback / interrupt_function arguments: a callback that never fires changes nothing ...
+    calls = []
+    states2 = init.copy()
+    e2, _, done2 = gpu_ctx.sample_ising(m.h, m.starts, m.ends, m.weights, states2, betas, spb, seeds,
+                                        interrupt_function=lambda: calls.append(1) and False)
+    assert done2 == 40 and np.array_equal(states2, ref) and np.array_equal(e2.view(np.uint64), ref_e.view(np.uint64))
+    # ... and one that fires stops the run between read waves (a launch that is already over completes): the completed reads
+    # equal the oracle's
+    big = schedule.random_spin_states(6000, m.num_variables, 3)
+    bseeds = schedule.per_read_seeds(3, 6000)
+    bref = big[:64].copy()
+    bref_e, _ = oracle.sample_ising(m.h, m.starts, m.ends, m.weights, bref, betas, spb, bseeds[:64])
+    e3, _, done3 = gpu_ctx.sample_ising(m.h, m.starts, m.ends, m.weights, big, betas, spb, bseeds, interrupt_function=lambda: True)
+    assert 64 <= done3 <= 6000
+    assert np.array_equal(big[:64], bref) and np.array_equal(e3[:64].view(np.uint64), bref_e.view(np.uint64))
 
 
 def test_energy_argmin_kernel(gpu_ctx, graph256):
