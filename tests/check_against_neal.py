@@ -4,7 +4,7 @@ The CPU oracle (oracle/cpu_sa_ref.cpp) restates neal's `cpu_sa.cpp` from the pub
 repo is GPU == oracle.  This script checks the remaining link on a machine that has `dimod` and `dwave-neal` (or
 `dwave-samplers`) installed:
 
-    python tools/check_against_neal.py            # exits 0 when every case matches bit for bit, 1 otherwise, 2 if neal is absent
+    python tests/check_against_neal.py            # exits 0 when every case matches bit for bit, 1 otherwise, 2 if neal is absent
 
 For each case it builds a spin model, lets dimod produce neal's vectors (`to_numpy_vectors`, the order neal itself uses), runs
 
