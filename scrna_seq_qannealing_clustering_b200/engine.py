@@ -384,9 +384,10 @@ class DeviceGraph:
         return self.num_nodes(problem), int(eu.value or 0), int(ev.value or 0), int(w.value or 0), self.num_edges(problem)
 
     def close(self):
-        if getattr(self, "_h", None):
+        # the native object points at its context: once that is gone (interpreter shutdown order) leak rather than touch it
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             _lib.load().qa_graph_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -484,9 +485,10 @@ class IsingModel:
         return energies, float(be.value), int(bi.value), st
 
     def close(self):
-        if getattr(self, "_h", None):
+        # the native object points at its context: once that is gone (interpreter shutdown order) leak rather than touch it
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             _lib.load().qa_model_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
