@@ -242,3 +242,24 @@ def test_known_answer_energies():
     # noisy_circles: component split has cut = 0 and perfect balance -> provably optimal E* = -gamma n^2 / 4
     k = known["noisy_circles"]
     assert k["E_largest_component"] == pytest.approx(k["lower_bound"], rel=1e-14)
+
+
+def test_dense_kway_builder_equals_the_dqm_builder_on_a_complete_graph():
+    """models.dense_kway_model (BASELINE config 5) emits, without a networkx round trip, exactly the couplers of
+    dqm_model(..., semantics='intended', structured=False) on the complete graph of the affinity matrix -- same order, same bits;
+    the linear part differs only by the summation order of the weighted degrees."""
+    from scrna_seq_qannealing_clustering_b200 import snn
+    X, _ = snn.gaussian_mixture_embedding(36, dim=6, centres=3, seed=2)
+    A = snn.gaussian_affinity(X, k=5)
+    G = nx.Graph()
+    G.add_nodes_from(str(i) for i in range(len(X)))
+    for i in range(len(X)):
+        for j in range(i):
+            G.add_edge(str(j), str(i), weight=float(A[i, j]))
+    for K in (1, 2, 4):
+        a = models.dqm_model(G, K, 0.05, penalty=30.0, semantics="intended", structured=False)
+        b = models.dense_kway_model(A, K, 0.05, penalty=30.0)
+        assert np.array_equal(a.starts, b.starts) and np.array_equal(a.ends, b.ends)
+        assert np.array_equal(a.weights.view(np.uint64), b.weights.view(np.uint64))
+        assert np.allclose(a.h, b.h, rtol=0, atol=1e-12) and a.offset == pytest.approx(b.offset, abs=1e-9)
+        assert b.meta["num_cases"] == K and b.meta["dense"] is True
